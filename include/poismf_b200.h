@@ -1,0 +1,123 @@
+/* poismf_b200 — C ABI of the B200-native poismf hot path (libpoismf_b200.so).
+ *
+ * Plain C symbols, plain pointers and sizes: this is the boundary a maintainer of
+ * david-cortes/poismf binds instead of compiling src/poismf.c, src/pred.c and
+ * src/topN.c into the wrapper.  Every entry point names the
+ * reference interface it replaces.
+ *
+ * Value types:  PMF_F32 <-> real_t=float  (-DUSE_FLOAT, src/poismf.h:100-108)
+ *               PMF_F64 <-> real_t=double (src/poismf.h:91-99)
+ * Index types:  index_bytes = 8 <-> sparse_ix=size_t (Python, src/poismf.h:76)
+ *               index_bytes = 4 <-> sparse_ix=int    (R,      src/poismf.h:86)
+ *
+ * Return codes follow the reference: 0 ok, 1 out of memory / CUDA failure,
+ * 2 interrupted (run) or invalid arguments (topN).  There is no CPU fallback: if
+ * no CUDA device is usable every compute entry point fails with 1 and a message
+ * on stderr.
+ */
+#ifndef POISMF_B200_H
+#define POISMF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PMF_F32 = 0, PMF_F64 = 1 };
+enum { PMF_TNCG = 1, PMF_CG = 2, PMF_PG = 3 };          /* == Method, src/poismf.h:225 */
+enum { PMF_SIDE_CSR = 0, PMF_SIDE_CSC = 1 };            /* CSR drives the A update, CSC the B update */
+
+/* Numerics-mode flags (argument `flags`, or env POISMF_B200_FLAGS for the drop-in calls) */
+enum {
+    PMF_FLAG_STRICT    = 1,  /* sequential sums, no FMA: mimics the reference built with naive BLAS */
+    PMF_FLAG_NO_CACHED = 2   /* cg: recompute every line-search objective from the factors        */
+};
+
+/* Hyper-parameters of a fit; same meaning as the arguments of run_poismf
+ * (src/poismf.h:226-233, documented at src/poismf.c:407-434). */
+typedef struct pmf_b200_params {
+    double l2_reg, l1_reg, w_mult, step_size;
+    int method;            /* PMF_TNCG / PMF_CG / PMF_PG */
+    int limit_step;
+    size_t numiter, maxupd;
+    int early_stop, reuse_prev;
+    int flags;             /* PMF_FLAG_* */
+} pmf_b200_params;
+
+typedef struct pmf_b200_handle pmf_b200_handle;
+
+/* ---- library ------------------------------------------------------------ */
+int         pmf_b200_device_count(void);          /* 0 when no usable CUDA device */
+const char* pmf_b200_last_error(void);            /* message of the last failure on this thread */
+uint64_t    pmf_b200_kernel_launches(void);       /* kernels launched by this library so far */
+
+/* ---- device-resident fit (what run_poismf does between its H2D and D2H) --- */
+/* A handle owns the device copy of one problem: factors A [dimA x k], B [dimB x k]
+ * (stored with a row stride of ldf = k rounded up to 16 bytes, pads zero) and the
+ * count matrix in CSR and CSC.  For sharded fits a handle holds only the rows
+ * [row_begin,row_end) of each compressed matrix but full replicas of A and B. */
+pmf_b200_handle* pmf_b200_create(int dtype, size_t dimA, size_t dimB, size_t k, int device);
+void pmf_b200_destroy(pmf_b200_handle* h);
+int  pmf_b200_ldf(const pmf_b200_handle* h);       /* device row stride of A and B, in elements */
+
+/* Upload one orientation of X from HOST arrays laid out as the reference expects
+ * (values real_t[nnz]; indptr sparse_ix[n_rows+1] relative to the first local row;
+ * indices sparse_ix[nnz]).  row_begin/n_rows select the shard (0, dim for a full fit). */
+int pmf_b200_set_matrix(pmf_b200_handle* h, int side, const void* values, const void* indptr,
+                        const void* indices, size_t nnz, int index_bytes,
+                        size_t row_begin, size_t n_rows);
+int pmf_b200_set_factors(pmf_b200_handle* h, const void* A_host, const void* B_host);  /* H2D, dense [dim x k] */
+int pmf_b200_get_factors(pmf_b200_handle* h, void* A_host, void* B_host);              /* D2H, dense [dim x k] */
+/* Use caller-owned DEVICE buffers ([dim x ldf], pads zero) for A and B, e.g. torch tensors. */
+int pmf_b200_bind_factors(pmf_b200_handle* h, void* A_dev, void* B_dev);
+void* pmf_b200_factor_ptr(pmf_b200_handle* h, int which /*0=A,1=B*/);
+int pmf_b200_set_stream(pmf_b200_handle* h, void* cuda_stream);   /* e.g. torch's current stream */
+
+/* numiter full alternating sweeps (src/poismf.c:506-608) on the device copy.
+ * Asynchronous on the handle's stream except for tncg early stopping. */
+int pmf_b200_sweeps(pmf_b200_handle* h, const pmf_b200_params* p);
+/* One half-sweep, for the sharding layer (poismf_b200/sharding.py): updates the
+ * local rows of B (side=CSC) or A (side=CSR).  `step_size` is the CURRENT pg step
+ * (the caller applies the halving of src/poismf.c:532); `first_half` tells the pg
+ * column-sum scaling of src/poismf.c:523-524 from the one of :573-577.
+ * *converged (may be NULL) receives the tncg early-stop verdict's numerator: the
+ * number of local rows that moved less than 1e-4 (src/poismf.c:393-396). */
+int pmf_b200_half_sweep(pmf_b200_handle* h, int side, const pmf_b200_params* p, double step_size,
+                        double cnst_div, unsigned long long* n_unchanged);
+int pmf_b200_sync(pmf_b200_handle* h);
+
+/* ---- drop-in entry points (host pointers in, host pointers out) ---------- */
+/* Replaces run_poismf, src/poismf.c:435-632 (prototype src/poismf.h:226-233). */
+int pmf_b200_run_poismf(int dtype, int index_bytes,
+                        void* A, const void* Xr, const void* Xr_indptr, const void* Xr_indices,
+                        void* B, const void* Xc, const void* Xc_indptr, const void* Xc_indices,
+                        size_t dimA, size_t dimB, size_t k,
+                        double l2_reg, double l1_reg, double w_mult, double step_size,
+                        int method, int limit_step, size_t numiter, size_t maxupd,
+                        int early_stop, int reuse_prev, int handle_interrupt, int flags);
+
+/* Replaces predict_multiple, src/pred.c:42-64 (prototype src/poismf.h:250-257). */
+int pmf_b200_predict_multiple(int dtype, int index_bytes, void* out, const void* A, const void* B,
+                              const void* ixA, const void* ixB, size_t n, int k,
+                              size_t dimA, size_t dimB);
+
+/* Replaces topN, src/topN.c:112-284 (prototype src/poismf.h:240-247) for ONE user. */
+int pmf_b200_topN(int dtype, int index_bytes, const void* a_vec, const void* B, int k,
+                  const void* include_ix, size_t n_include, const void* exclude_ix, size_t n_exclude,
+                  void* outp_ix, void* outp_score, size_t n_top, size_t n);
+
+/* Batched top-N: scores `n_users` rows of A (selected by user_ix, or rows 0..n_users-1
+ * when NULL) against all n items of B, excluding per user the item ids
+ * excl_ix[excl_ptr[u] .. excl_ptr[u+1]) (both may be NULL).  Output is
+ * [n_users x n_top] item ids (sparse_ix) and optionally scores.  No reference
+ * equivalent: the reference loops topN per user (poismf/__init__.py:914-923). */
+int pmf_b200_topN_batch(int dtype, int index_bytes, const void* A, const void* B, int k,
+                        const void* user_ix, size_t n_users, size_t dimA,
+                        const void* excl_ptr, const void* excl_ix,
+                        void* outp_ix, void* outp_score, size_t n_top, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POISMF_B200_H */

@@ -1,0 +1,794 @@
+// poismf_b200 — host side of libpoismf_b200.so: device handle, row planner,
+// sweep driver and the C ABI declared in include/poismf_b200.h.
+//
+// The sweep driver restates run_poismf's outer loop (/root/reference/src/poismf.c:506-608)
+// around device kernels: column sums -> (zero empty rows) -> binned row solvers,
+// B side over CSC first, then A side over CSR, with pg's step halving between
+// the two half-sweeps and tncg's early-stop bookkeeping.
+#include <algorithm>
+#include <atomic>
+#include <csignal>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "../../include/poismf_b200.h"
+#include "aux_kernels.cuh"
+#include "kernels.cuh"
+#include "launch.h"
+
+using namespace pmf;
+
+// ---------------------------------------------------------------------------
+// errors, counters, interrupt flag
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+static volatile sig_atomic_t g_interrupted = 0;
+
+static int fail(const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    fprintf(stderr, "poismf_b200: %s\n", buf);
+    return 1;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                    \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+extern "C" const char* pmf_b200_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t pmf_b200_kernel_launches(void) { return g_launches.load(); }
+extern "C" int pmf_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline size_t round_up_sz(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// tile row stride: a multiple of 16 bytes whose 16-byte-unit count is odd, so that
+// 16-byte accesses of consecutive lanes to consecutive tile rows hit distinct banks
+static int tile_stride(int k, int V)
+{
+    int units = (k + V - 1) / V;
+    if (units % 2 == 0) units++;
+    return units * V;
+}
+
+// ---------------------------------------------------------------------------
+// one orientation (CSR or CSC) of the count matrix on the device + its row plan
+// ---------------------------------------------------------------------------
+struct Bin {
+    bool block = false;     // CTA per row (else warp per row)
+    int cap = 0;            // staged tile capacity; 0 = tile stays in global memory
+    int threads = 256;
+    size_t slice = 0, smem = 0;
+    std::vector<int> rows;  // local row ids, longest first
+    int* d_rows = nullptr;
+    long long max_nnz = 0;
+};
+
+template <class real> struct Side {
+    real* xv = nullptr;
+    long long* ptr = nullptr;
+    int* ind = nullptr;
+    size_t nnz = 0, row_begin = 0, n_rows = 0;
+    std::vector<long long> h_ptr;
+    std::vector<Bin> bins;
+    int planned_method = -1;
+    int* d_empty = nullptr;
+    int n_empty = 0;
+    int* d_all_rows = nullptr;
+    real* gscratch = nullptr;
+    long long gs_stride = 0;
+    int gs_ctas = 0;
+    void free_plan()
+    {
+        if (d_all_rows) cudaFree(d_all_rows);
+        if (gscratch) cudaFree(gscratch);
+        d_all_rows = nullptr; gscratch = nullptr; d_empty = nullptr;
+        bins.clear(); planned_method = -1;
+    }
+    void free_all()
+    {
+        free_plan();
+        if (xv) cudaFree(xv);
+        if (ptr) cudaFree(ptr);
+        if (ind) cudaFree(ind);
+        xv = nullptr; ptr = nullptr; ind = nullptr;
+    }
+};
+
+struct pmf_b200_handle {
+    int dtype = 0, device = 0;
+    size_t dimA = 0, dimB = 0;
+    int k = 0, kp = 0, ldf = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    virtual ~pmf_b200_handle() {}
+    virtual int set_matrix(int side, const void* values, const void* indptr, const void* indices, size_t nnz,
+                           int index_bytes, size_t row_begin, size_t n_rows) = 0;
+    virtual int set_factors(const void* A, const void* B) = 0;
+    virtual int get_factors(void* A, void* B) = 0;
+    virtual int bind_factors(void* A, void* B) = 0;
+    virtual void* factor_ptr(int which) = 0;
+    virtual int half_sweep(int side, const pmf_b200_params& p, double step, double cdiv,
+                           unsigned long long* n_unchanged) = 0;
+    virtual int sweeps(const pmf_b200_params& p) = 0;
+};
+
+static const size_t SMEM_PER_SM = 233472;     // 228 KB
+static const size_t SMEM_CTA_MAX = 232448;    // 227 KB opt-in maximum per CTA
+static const size_t SMEM_CTA_RESERVED = 1024; // per-CTA system reservation
+
+template <class real> struct HandleT : pmf_b200_handle {
+    real *A = nullptr, *B = nullptr;
+    bool ownA = false, ownB = false;
+    Side<real> sides[2];
+    real* csum = nullptr;       // k
+    real* partial = nullptr;    // colsum partials
+    int n_partial = 0;
+    int* counters = nullptr;    // one per bin
+    unsigned long long* d_unchanged = nullptr;
+    static constexpr int V = RealTraits<real>::V;
+
+    ~HandleT() override
+    {
+        cudaSetDevice(device);
+        sides[0].free_all(); sides[1].free_all();
+        if (ownA && A) cudaFree(A);
+        if (ownB && B) cudaFree(B);
+        if (csum) cudaFree(csum);
+        if (partial) cudaFree(partial);
+        if (counters) cudaFree(counters);
+        if (d_unchanged) cudaFree(d_unchanged);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    int init()
+    {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        num_sms = prop.multiProcessorCount;
+        ldf = round_up(k, V);
+        kp = tile_stride(k, V);
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+        CK(cudaMalloc(&A, dimA * (size_t)ldf * sizeof(real)));
+        ownA = true;
+        CK(cudaMalloc(&B, dimB * (size_t)ldf * sizeof(real)));
+        ownB = true;
+        CK(cudaMemsetAsync(A, 0, dimA * (size_t)ldf * sizeof(real), stream));
+        CK(cudaMemsetAsync(B, 0, dimB * (size_t)ldf * sizeof(real), stream));
+        CK(cudaMalloc(&csum, (size_t)kp * sizeof(real)));
+        n_partial = num_sms * 4;
+        CK(cudaMalloc(&partial, (size_t)n_partial * ldf * sizeof(real)));
+        CK(cudaMalloc(&counters, 64 * sizeof(int)));
+        CK(cudaMalloc(&d_unchanged, sizeof(unsigned long long)));
+        return 0;
+    }
+
+    template <class IX>
+    int upload_side(Side<real>& S, const real* values, const IX* indptr, const IX* indices, size_t nnz, size_t n_rows)
+    {
+        S.h_ptr.resize(n_rows + 1);
+        const long long base = (long long)indptr[0];
+        for (size_t i = 0; i <= n_rows; i++) S.h_ptr[i] = (long long)indptr[i] - base;
+        if ((size_t)S.h_ptr[n_rows] != nnz) return fail("set_matrix: indptr[n_rows]-indptr[0] != nnz");
+        CK(cudaMalloc(&S.xv, std::max<size_t>(nnz, 1) * sizeof(real)));
+        CK(cudaMalloc(&S.ind, std::max<size_t>(nnz, 1) * sizeof(int)));
+        CK(cudaMalloc(&S.ptr, (n_rows + 1) * sizeof(long long)));
+        CK(cudaMemcpyAsync(S.xv, values, nnz * sizeof(real), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(S.ptr, S.h_ptr.data(), (n_rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        // indices: upload at host width, narrow to int32 on the device
+        if (sizeof(IX) == sizeof(int)) {
+            CK(cudaMemcpyAsync(S.ind, indices, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+        } else {
+            IX* tmp = nullptr;
+            const size_t chunk = (size_t)1 << 27;   // bounded staging buffer (1 GiB of 8-byte ids)
+            CK(cudaMalloc(&tmp, std::min(chunk, std::max<size_t>(nnz, 1)) * sizeof(IX)));
+            for (size_t off = 0; off < nnz; off += chunk) {
+                const size_t m = std::min(chunk, nnz - off);
+                CK(cudaMemcpyAsync(tmp, indices + off, m * sizeof(IX), cudaMemcpyHostToDevice, stream));
+                narrow_indices_kernel<IX><<<num_sms * 8, 256, 0, stream>>>(tmp, S.ind + off, m);
+                LAUNCHED();
+                CK(cudaGetLastError());
+            }
+            CK(cudaStreamSynchronize(stream));
+            cudaFree(tmp);
+        }
+        CK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+
+    int set_matrix(int side, const void* values, const void* indptr, const void* indices, size_t nnz,
+                   int index_bytes, size_t row_begin, size_t n_rows) override
+    {
+        CK(cudaSetDevice(device));
+        if (side != 0 && side != 1) return fail("set_matrix: bad side");
+        const size_t dim = side == PMF_SIDE_CSR ? dimA : dimB;
+        if (row_begin + n_rows > dim) return fail("set_matrix: row range exceeds the dimension");
+        Side<real>& S = sides[side];
+        S.free_all();
+        S.nnz = nnz; S.row_begin = row_begin; S.n_rows = n_rows;
+        if (index_bytes == 8)
+            return upload_side<uint64_t>(S, (const real*)values, (const uint64_t*)indptr, (const uint64_t*)indices, nnz, n_rows);
+        if (index_bytes == 4)
+            return upload_side<int>(S, (const real*)values, (const int*)indptr, (const int*)indices, nnz, n_rows);
+        return fail("set_matrix: index_bytes must be 4 or 8");
+    }
+
+    int set_factors(const void* Ah, const void* Bh) override
+    {
+        CK(cudaSetDevice(device));
+        const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
+        if (Ah) CK(cudaMemcpy2DAsync(A, pitch, Ah, w, w, dimA, cudaMemcpyHostToDevice, stream));
+        if (Bh) CK(cudaMemcpy2DAsync(B, pitch, Bh, w, w, dimB, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    int get_factors(void* Ah, void* Bh) override
+    {
+        CK(cudaSetDevice(device));
+        const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
+        if (Ah) CK(cudaMemcpy2DAsync(Ah, w, A, pitch, w, dimA, cudaMemcpyDeviceToHost, stream));
+        if (Bh) CK(cudaMemcpy2DAsync(Bh, w, B, pitch, w, dimB, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    int bind_factors(void* Ad, void* Bd) override
+    {
+        CK(cudaSetDevice(device));
+        if (Ad) { if (ownA && A) cudaFree(A); A = (real*)Ad; ownA = false; }
+        if (Bd) { if (ownB && B) cudaFree(B); B = (real*)Bd; ownB = false; }
+        return 0;
+    }
+    void* factor_ptr(int which) override { return which == 0 ? (void*)A : (void*)B; }
+
+    // ---- planner: bin the local rows of one side by non-zero count -------------
+    size_t slice_bytes(int team_threads, int nvec, int cap) const
+    {
+        size_t b = 288 + (size_t)team_threads * 16 + (size_t)nvec * kp * sizeof(real) +
+                   (size_t)4 * cap * sizeof(real) + (size_t)cap * kp * sizeof(real);
+        return round_up_sz(b, 16);
+    }
+    int plan(Side<real>& S, int method)
+    {
+        if (S.planned_method == method) return 0;
+        S.free_plan();
+        const int nvec = method == PMF_PG ? 3 : (method == PMF_CG ? 7 : TN_NUM_VECS);
+        std::vector<Bin> bins;
+        // warp-per-row bins
+        const int wcaps[3] = {32, 64, 128};
+        for (int c = 0; c < 3; c++) {
+            Bin b;
+            b.block = false; b.cap = wcaps[c];
+            b.slice = slice_bytes(32, nvec, b.cap);
+            int warps = 8;
+            while (warps > 1 && b.slice * warps > SMEM_CTA_MAX) warps >>= 1;
+            if (b.slice * warps > SMEM_CTA_MAX) continue;
+            b.threads = warps * 32;
+            b.smem = b.slice * warps;
+            bins.push_back(b);
+        }
+        // CTA-per-row bins: largest capacity with 4, 2, 1 resident CTAs per SM
+        const int ctas[3] = {4, 2, 1};
+        int last_cap = bins.empty() ? 0 : bins.back().cap;
+        for (int c = 0; c < 3; c++) {
+            const size_t budget = std::min(SMEM_CTA_MAX, SMEM_PER_SM / ctas[c] - SMEM_CTA_RESERVED);
+            const size_t fixed = slice_bytes(256, nvec, 0) + 16;
+            if (budget <= fixed) continue;
+            int cap = (int)((budget - fixed) / ((size_t)(kp + 4) * sizeof(real)));
+            cap = cap / 4 * 4;
+            if (cap <= last_cap) continue;
+            Bin b;
+            b.block = true; b.cap = cap; b.threads = 256;
+            b.slice = slice_bytes(256, nvec, cap);
+            b.smem = b.slice;
+            bins.push_back(b);
+            last_cap = cap;
+        }
+        {   // everything longer: tile stays in global memory / L2
+            Bin b;
+            b.block = true; b.cap = 0; b.threads = 256;
+            b.slice = slice_bytes(256, nvec, 0);
+            b.smem = b.slice;
+            bins.push_back(b);
+        }
+        std::vector<int> empty;
+        for (size_t r = 0; r < S.n_rows; r++) {
+            const long long n = S.h_ptr[r + 1] - S.h_ptr[r];
+            if (n == 0) { empty.push_back((int)r); continue; }
+            size_t bi = 0;
+            while (bi + 1 < bins.size() && n > bins[bi].cap) bi++;
+            bins[bi].rows.push_back((int)r);
+            bins[bi].max_nnz = std::max(bins[bi].max_nnz, n);
+        }
+        size_t total = empty.size();
+        for (auto& b : bins) {
+            std::stable_sort(b.rows.begin(), b.rows.end(), [&](int a, int c) {
+                return (S.h_ptr[a + 1] - S.h_ptr[a]) > (S.h_ptr[c + 1] - S.h_ptr[c]);
+            });
+            total += b.rows.size();
+        }
+        CK(cudaMalloc(&S.d_all_rows, std::max<size_t>(total, 1) * sizeof(int)));
+        size_t off = 0;
+        for (auto& b : bins) {
+            b.d_rows = S.d_all_rows + off;
+            if (!b.rows.empty())
+                CK(cudaMemcpyAsync(b.d_rows, b.rows.data(), b.rows.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            off += b.rows.size();
+        }
+        S.d_empty = S.d_all_rows + off;
+        S.n_empty = (int)empty.size();
+        if (!empty.empty())
+            CK(cudaMemcpyAsync(S.d_empty, empty.data(), empty.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        const Bin& gb = bins.back();
+        if (!gb.rows.empty()) {
+            S.gs_stride = (long long)round_up_sz((size_t)gb.max_nnz, 4);
+            S.gs_ctas = (int)std::min<size_t>(gb.rows.size(), (size_t)num_sms);
+            CK(cudaMalloc(&S.gscratch, (size_t)S.gs_ctas * 3 * S.gs_stride * sizeof(real)));
+        }
+        CK(cudaStreamSynchronize(stream));
+        S.bins.swap(bins);
+        S.planned_method = method;
+        return 0;
+    }
+
+    // ---- column sums of the fixed factor matrix -------------------------------
+    int column_sums(const real* F, size_t nrow, const ColsumFinal<real>& fin, bool strict)
+    {
+        if (strict) {
+            colsum_seq_kernel<real><<<(k + 63) / 64, 64, 0, stream>>>(F, nrow, k, ldf, fin, csum);
+            LAUNCHED();
+        } else {
+            const int threads = 256;
+            if (ldf > threads) return fail("k too large for the column-sum kernel");
+            const int rpb = threads / ldf;
+            int grid = (int)std::min<size_t>((size_t)n_partial, (nrow + rpb - 1) / rpb);
+            grid = std::max(grid, 1);
+            colsum_partial_kernel<real><<<grid, threads, threads * sizeof(real), stream>>>(F, nrow, ldf, partial);
+            LAUNCHED();
+            colsum_fold_kernel<real><<<(k + 63) / 64, 64, 0, stream>>>(partial, grid, k, ldf, fin, csum);
+            LAUNCHED();
+        }
+        CK(cudaGetLastError());
+        return 0;
+    }
+
+    // ---- one half-sweep ----------------------------------------------------------
+    // side CSC: update local rows of B with A fixed (src/poismf.c:510-557)
+    // side CSR: update local rows of A with B fixed (:561-604)
+    int half_sweep(int side, const pmf_b200_params& p, double step_d, double cdiv_d,
+                   unsigned long long* n_unchanged) override
+    {
+        CK(cudaSetDevice(device));
+        Side<real>& S = sides[side];
+        if (!S.ptr) return fail("half_sweep: matrix for side %d not set", side);
+        if (p.method != PMF_PG && p.method != PMF_CG && p.method != PMF_TNCG) return fail("bad method");
+        if (plan(S, p.method)) return 1;
+        const bool strict = (p.flags & PMF_FLAG_STRICT) != 0;
+        const bool updA = side == PMF_SIDE_CSR;
+        real* M = updA ? A : B;
+        const real* F = updA ? B : A;
+        const size_t other = updA ? dimB : dimA;
+
+        const real l2 = (real)p.l2_reg, l1 = (real)p.l1_reg, w = (real)p.w_mult, step = (real)step_d;
+        HalfSweepConsts<real> hc;
+        hc.l2 = l2;
+        hc.two_l2 = (real)(2. * (double)l2);
+        hc.w = w;
+        hc.wm1 = (real)((double)w - 1.);
+        hc.step_w = step * w;
+        hc.neg_step = -step;
+        hc.cdiv = (real)cdiv_d;
+        hc.maxupd = (int)std::min<size_t>(p.maxupd, (size_t)INT32_MAX);
+        hc.limit_step = p.limit_step; hc.reuse_prev = p.reuse_prev;
+        hc.early_stop = (p.method == PMF_TNCG && p.early_stop) ? 1 : 0;
+        hc.method = p.method;
+
+        ColsumFinal<real> fin;
+        fin.l1 = l1; fin.scale1 = -step; fin.scale2 = -step; fin.nscale = 0;
+        if (p.method == PMF_PG && w == (real)1) fin.nscale = updA ? 2 : 1;   // Q1: A side scaled twice
+        if (column_sums(F, other, fin, strict)) return 1;
+
+        if (S.n_empty > 0) {
+            const size_t total = (size_t)S.n_empty * ldf;
+            const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms * 8);
+            zero_rows_kernel<real><<<grid, 256, 0, stream>>>(M + S.row_begin * (size_t)ldf, S.d_empty, S.n_empty, ldf);
+            LAUNCHED();
+        }
+        CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
+        if (hc.early_stop) CK(cudaMemsetAsync(d_unchanged, 0, sizeof(unsigned long long), stream));
+
+        for (int bi = (int)S.bins.size() - 1; bi >= 0; bi--) {    // heaviest rows first
+            const Bin& b = S.bins[bi];
+            if (b.rows.empty()) continue;
+            SideParams<real> P;
+            P.M = M + S.row_begin * (size_t)ldf;
+            P.F = F; P.xv = S.xv; P.ptr = S.ptr; P.ind = S.ind; P.csum = csum;
+            P.rows = b.d_rows; P.nrows = (int)b.rows.size();
+            P.counter = counters + bi;
+            P.k = k; P.kp = kp; P.ldf = ldf; P.cap = b.cap; P.slice_bytes = (int)b.slice;
+            P.hc = hc;
+            P.gscratch = b.cap == 0 ? S.gscratch : nullptr;
+            P.gs_stride = S.gs_stride;
+            P.n_unchanged = d_unchanged;
+            LaunchCfg cfg;
+            cfg.block_team = b.block;
+            cfg.cached = !strict && !(p.flags & PMF_FLAG_NO_CACHED);
+            cfg.threads = b.threads;
+            cfg.smem_bytes = b.smem;
+            cfg.stream = stream;
+            const int warps = b.threads / 32;
+            cfg.needed = b.block ? P.nrows : (P.nrows + warps - 1) / warps;
+            cfg.max_grid = b.cap == 0 ? S.gs_ctas : (1 << 30);
+            cfg.num_sms = num_sms;
+            cudaError_t e;
+            if (p.method == PMF_TNCG)
+                e = strict ? launch_rows_tn_strict<real>(cfg, P) : launch_rows_tn_fast<real>(cfg, P);
+            else
+                e = strict ? launch_rows_pgcg_strict<real>(cfg, P) : launch_rows_pgcg_fast<real>(cfg, P);
+            LAUNCHED();
+            if (e != cudaSuccess) return fail("row kernel launch failed: %s", cudaGetErrorString(e));
+        }
+        if (hc.early_stop && n_unchanged) {
+            CK(cudaMemcpyAsync(n_unchanged, d_unchanged, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+        return 0;
+    }
+
+    // ---- numiter alternating sweeps (src/poismf.c:506-608) -------------------------
+    int sweeps(const pmf_b200_params& p) override
+    {
+        // the reference carries step_size as real_t: round it the same way
+        real step = (real)p.step_size;
+        const real l2 = (real)p.l2_reg;
+        bool stopA = false, stopB = false;
+        if (sides[0].n_rows != dimA || sides[1].n_rows != dimB)
+            return fail("sweeps: handle holds a shard; drive it with pmf_b200_half_sweep");
+        for (size_t it = 0; it < p.numiter; it++) {
+            if (g_interrupted) return 2;
+            const double cdiv = (double)(real)(1. / (1. + 2. * (double)l2 * (double)step));   // :511
+            unsigned long long unch = 0;
+            if (!(p.method == PMF_TNCG && stopB)) {
+                if (half_sweep(PMF_SIDE_CSC, p, (double)step, cdiv, &unch)) return 1;
+                if (p.method == PMF_TNCG && p.early_stop)
+                    stopB = ((double)unch / (double)dimB) >= .95;                             // :402
+            }
+            if (p.method == PMF_PG) step = (real)((double)step * 0.5);                        // :532
+            if (g_interrupted) return 2;
+            if (!(p.method == PMF_TNCG && stopA)) {
+                if (half_sweep(PMF_SIDE_CSR, p, (double)step, cdiv, &unch)) return 1;
+                if (p.method == PMF_TNCG && p.early_stop)
+                    stopA = ((double)unch / (double)dimA) >= .95;
+            }
+            if (stopA && stopB) break;                                                        // :606
+        }
+        return 0;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" pmf_b200_handle* pmf_b200_create(int dtype, size_t dimA, size_t dimB, size_t k, int device)
+{
+    if (pmf_b200_device_count() <= 0) {
+        fail("no usable CUDA device: poismf_b200 has no CPU fallback");
+        return nullptr;
+    }
+    if (k == 0 || k > 256) { fail("k must be in [1, 256]"); return nullptr; }
+    if (dimA > (size_t)INT32_MAX || dimB > (size_t)INT32_MAX) { fail("dimensions must be <= 2^31-1"); return nullptr; }
+    pmf_b200_handle* h = nullptr;
+    if (dtype == PMF_F32) h = new HandleT<float>();
+    else if (dtype == PMF_F64) h = new HandleT<double>();
+    else { fail("bad dtype"); return nullptr; }
+    h->dtype = dtype; h->device = device; h->dimA = dimA; h->dimB = dimB; h->k = (int)k;
+    int rc = dtype == PMF_F32 ? static_cast<HandleT<float>*>(h)->init() : static_cast<HandleT<double>*>(h)->init();
+    if (rc) { delete h; return nullptr; }
+    return h;
+}
+extern "C" void pmf_b200_destroy(pmf_b200_handle* h) { delete h; }
+extern "C" int pmf_b200_ldf(const pmf_b200_handle* h) { return h->ldf; }
+extern "C" int pmf_b200_set_matrix(pmf_b200_handle* h, int side, const void* values, const void* indptr,
+                                   const void* indices, size_t nnz, int index_bytes, size_t row_begin, size_t n_rows)
+{
+    return h->set_matrix(side, values, indptr, indices, nnz, index_bytes, row_begin, n_rows);
+}
+extern "C" int pmf_b200_set_factors(pmf_b200_handle* h, const void* A, const void* B) { return h->set_factors(A, B); }
+extern "C" int pmf_b200_get_factors(pmf_b200_handle* h, void* A, void* B) { return h->get_factors(A, B); }
+extern "C" int pmf_b200_bind_factors(pmf_b200_handle* h, void* A, void* B) { return h->bind_factors(A, B); }
+extern "C" void* pmf_b200_factor_ptr(pmf_b200_handle* h, int which) { return h->factor_ptr(which); }
+extern "C" int pmf_b200_set_stream(pmf_b200_handle* h, void* s)
+{
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = (cudaStream_t)s;
+    h->own_stream = false;
+    return 0;
+}
+extern "C" int pmf_b200_sweeps(pmf_b200_handle* h, const pmf_b200_params* p) { return h->sweeps(*p); }
+extern "C" int pmf_b200_half_sweep(pmf_b200_handle* h, int side, const pmf_b200_params* p, double step_size,
+                                   double cnst_div, unsigned long long* n_unchanged)
+{
+    return h->half_sweep(side, *p, step_size, cnst_div, n_unchanged);
+}
+extern "C" int pmf_b200_sync(pmf_b200_handle* h)
+{
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- run_poismf drop-in ------------------------------------------------------
+static std::mutex g_sig_mutex;
+static bool g_sig_locked = false;
+static void on_sigint(int) { g_interrupted = 1; }
+
+static int env_flags(int flags)
+{
+    const char* e = getenv("POISMF_B200_FLAGS");
+    if (e && *e) flags |= atoi(e);
+    return flags;
+}
+static int env_device()
+{
+    const char* e = getenv("POISMF_B200_DEVICE");
+    return (e && *e) ? atoi(e) : 0;
+}
+
+extern "C" int pmf_b200_run_poismf(int dtype, int index_bytes,
+                                   void* A, const void* Xr, const void* Xr_indptr, const void* Xr_indices,
+                                   void* B, const void* Xc, const void* Xc_indptr, const void* Xc_indices,
+                                   size_t dimA, size_t dimB, size_t k,
+                                   double l2_reg, double l1_reg, double w_mult, double step_size,
+                                   int method, int limit_step, size_t numiter, size_t maxupd,
+                                   int early_stop, int reuse_prev, int handle_interrupt, int flags)
+{
+    // SIGINT handling as src/poismf.c:444-455,:618-630
+    void (*old_handler)(int) = nullptr;
+    bool have_lock = false;
+    {
+        std::lock_guard<std::mutex> g(g_sig_mutex);
+        if (!g_sig_locked) {
+            g_sig_locked = true; have_lock = true; g_interrupted = 0;
+            old_handler = signal(SIGINT, on_sigint);
+        }
+    }
+    int rc = 0;
+    pmf_b200_handle* h = pmf_b200_create(dtype, dimA, dimB, k, env_device());
+    if (!h) rc = 1;
+    const size_t isz = (size_t)index_bytes;
+    auto last = [&](const void* ptr, size_t n) -> size_t {
+        return isz == 8 ? (size_t)((const uint64_t*)ptr)[n] : (size_t)((const int*)ptr)[n];
+    };
+    if (!rc) rc = h->set_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, last(Xr_indptr, dimA), index_bytes, 0, dimA);
+    if (!rc) rc = h->set_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, last(Xc_indptr, dimB), index_bytes, 0, dimB);
+    if (!rc) rc = h->set_factors(A, B);
+    if (!rc) {
+        pmf_b200_params p;
+        p.l2_reg = l2_reg; p.l1_reg = l1_reg; p.w_mult = w_mult; p.step_size = step_size;
+        p.method = method; p.limit_step = limit_step; p.numiter = numiter; p.maxupd = maxupd;
+        p.early_stop = early_stop; p.reuse_prev = reuse_prev; p.flags = env_flags(flags);
+        rc = h->sweeps(p);
+        const int rc2 = (rc != 1) ? h->get_factors(A, B) : 0;   // interrupted fits still return usable factors
+        if (rc2) rc = 1;
+    }
+    if (h) pmf_b200_destroy(h);
+    if (rc == 1) fprintf(stderr, "Error: out of memory.\n");
+    {
+        std::lock_guard<std::mutex> g(g_sig_mutex);
+        const bool was_interrupted = g_interrupted != 0;
+        if (was_interrupted && rc != 1) { rc = 2; fprintf(stderr, "Error: procedure was interrupted\n"); }
+        if (have_lock) {
+            signal(SIGINT, old_handler);
+            g_sig_locked = false;
+            g_interrupted = 0;
+        }
+        if (was_interrupted && !handle_interrupt) raise(SIGINT);
+    }
+    return rc;
+}
+
+// ---- predict_multiple drop-in ------------------------------------------------
+template <class real, class IX>
+static int predict_impl(real* out, const real* A, const real* B, const IX* ixA, const IX* ixB, size_t n, int k,
+                        size_t dimA, size_t dimB)
+{
+    CK(cudaSetDevice(env_device()));
+    const int V = RealTraits<real>::V, ldf = round_up(k, V);
+    real *dA = nullptr, *dB = nullptr, *dout = nullptr;
+    IX *da = nullptr, *db = nullptr;
+    const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
+    int rc = 0;
+    auto body = [&]() -> int {
+        CK(cudaMalloc(&dA, dimA * pitch)); CK(cudaMalloc(&dB, dimB * pitch));
+        CK(cudaMalloc(&dout, std::max<size_t>(n, 1) * sizeof(real)));
+        CK(cudaMalloc(&da, std::max<size_t>(n, 1) * sizeof(IX))); CK(cudaMalloc(&db, std::max<size_t>(n, 1) * sizeof(IX)));
+        CK(cudaMemcpy2D(dA, pitch, A, w, w, dimA, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy2D(dB, pitch, B, w, w, dimB, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(da, ixA, n * sizeof(IX), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db, ixB, n * sizeof(IX), cudaMemcpyHostToDevice));
+        if (n) {
+            const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+            predict_pairs_kernel<real, IX><<<grid, 256>>>(dA, dB, da, db, n, k, ldf, dout);
+            LAUNCHED();
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpy(out, dout, n * sizeof(real), cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    rc = body();
+    cudaFree(dA); cudaFree(dB); cudaFree(dout); cudaFree(da); cudaFree(db);
+    return rc;
+}
+extern "C" int pmf_b200_predict_multiple(int dtype, int index_bytes, void* out, const void* A, const void* B,
+                                         const void* ixA, const void* ixB, size_t n, int k, size_t dimA, size_t dimB)
+{
+    if (pmf_b200_device_count() <= 0) return fail("no usable CUDA device: poismf_b200 has no CPU fallback");
+    if (dtype == PMF_F32 && index_bytes == 8) return predict_impl((float*)out, (const float*)A, (const float*)B, (const uint64_t*)ixA, (const uint64_t*)ixB, n, k, dimA, dimB);
+    if (dtype == PMF_F32 && index_bytes == 4) return predict_impl((float*)out, (const float*)A, (const float*)B, (const int*)ixA, (const int*)ixB, n, k, dimA, dimB);
+    if (dtype == PMF_F64 && index_bytes == 8) return predict_impl((double*)out, (const double*)A, (const double*)B, (const uint64_t*)ixA, (const uint64_t*)ixB, n, k, dimA, dimB);
+    if (dtype == PMF_F64 && index_bytes == 4) return predict_impl((double*)out, (const double*)A, (const double*)B, (const int*)ixA, (const int*)ixB, n, k, dimA, dimB);
+    return fail("predict_multiple: bad dtype/index width");
+}
+
+// ---- topN ----------------------------------------------------------------------
+// v1: exact scores (same sums as the reference) + CUB segmented radix sort.
+// Ranking = descending score; ties by ascending item id (the reference's tie order
+// is qsort's, i.e. unspecified).
+template <class real, class IX>
+static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_ix, size_t n_users, size_t dimA,
+                           const IX* excl_ptr, const IX* excl_ix, IX* outp_ix, real* outp_score, size_t n_top, size_t n,
+                           bool A_is_single_vector)
+{
+    CK(cudaSetDevice(env_device()));
+    if (n_top == 0 || n_top > n) return 2;
+    const int V = RealTraits<real>::V, ldf = round_up(k, V);
+    const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
+    // users per chunk: bound the score matrix to ~1 GiB
+    size_t chunk = std::max<size_t>(1, std::min<size_t>(n_users, ((size_t)1 << 28) / std::max<size_t>(n, 1)));
+    chunk = std::min<size_t>(chunk, 65535);
+    real *dB = nullptr, *dA = nullptr, *dAsel = nullptr, *sc_in = nullptr, *sc_out = nullptr;
+    int *id_in = nullptr, *id_out = nullptr, *seg = nullptr;
+    long long* dusers = nullptr;
+    IX *dexp = nullptr, *dexi = nullptr;
+    void* tmp = nullptr;
+    std::vector<int> h_ids(chunk * n_top);
+    std::vector<real> h_sc(chunk * n_top);
+    auto body = [&]() -> int {
+        const size_t rowsA = A_is_single_vector ? 1 : dimA;
+        CK(cudaMalloc(&dB, n * pitch)); CK(cudaMalloc(&dA, rowsA * pitch));
+        CK(cudaMemcpy2D(dB, pitch, B, w, w, n, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dA, 0, rowsA * pitch));
+        CK(cudaMemcpy2D(dA, pitch, A, w, w, rowsA, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&dAsel, chunk * pitch));
+        CK(cudaMalloc(&sc_in, chunk * n * sizeof(real))); CK(cudaMalloc(&sc_out, chunk * n * sizeof(real)));
+        CK(cudaMalloc(&id_in, chunk * n * sizeof(int))); CK(cudaMalloc(&id_out, chunk * n * sizeof(int)));
+        CK(cudaMalloc(&seg, (chunk + 1) * sizeof(int)));
+        CK(cudaMalloc(&dusers, chunk * sizeof(long long)));
+        std::vector<int> h_seg(chunk + 1);
+        for (size_t u = 0; u <= chunk; u++) h_seg[u] = (int)(u * n);
+        if (chunk * n > (size_t)INT32_MAX) return fail("topN: chunk too large");
+        CK(cudaMemcpy(seg, h_seg.data(), (chunk + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        size_t n_excl_total = 0;
+        if (excl_ptr && excl_ix) {
+            n_excl_total = (size_t)excl_ptr[n_users];
+            CK(cudaMalloc(&dexp, (n_users + 1) * sizeof(IX)));
+            CK(cudaMalloc(&dexi, std::max<size_t>(n_excl_total, 1) * sizeof(IX)));
+            CK(cudaMemcpy(dexp, excl_ptr, (n_users + 1) * sizeof(IX), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(dexi, excl_ix, n_excl_total * sizeof(IX), cudaMemcpyHostToDevice));
+        }
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tmp_bytes, sc_in, sc_out, id_in, id_out,
+                                                              (int)(chunk * n), (int)chunk, seg, seg + 1));
+        CK(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 1)));
+        for (size_t u0 = 0; u0 < n_users; u0 += chunk) {
+            const size_t m = std::min(chunk, n_users - u0);
+            std::vector<long long> hu(m);
+            for (size_t u = 0; u < m; u++) hu[u] = A_is_single_vector ? 0 : (user_ix ? (long long)user_ix[u0 + u] : (long long)(u0 + u));
+            CK(cudaMemcpy(dusers, hu.data(), m * sizeof(long long), cudaMemcpyHostToDevice));
+            gather_rows_kernel<real><<<(int)std::min<size_t>((m * ldf + 255) / 256, 4096), 256>>>(dA, dusers, (int)m, ldf, dAsel);
+            LAUNCHED();
+            dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 1024), (unsigned)m);
+            score_items_kernel<real><<<grid, 256, (size_t)ldf * sizeof(real)>>>(dAsel, dB, n, k, ldf, sc_in, id_in);
+            LAUNCHED();
+            if (dexp) {
+                dim3 g2(8, (unsigned)m);
+                mask_excluded_kernel<real, IX><<<g2, 256>>>(sc_in, n, dexp, dexi, u0);
+                LAUNCHED();
+            }
+            CK(cudaGetLastError());
+            CK(cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp, tmp_bytes, sc_in, sc_out, id_in, id_out,
+                                                                  (int)(m * n), (int)m, seg, seg + 1));
+            LAUNCHED();
+            CK(cudaMemcpy2D(h_ids.data(), n_top * sizeof(int), id_out, n * sizeof(int), n_top * sizeof(int), m, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy2D(h_sc.data(), n_top * sizeof(real), sc_out, n * sizeof(real), n_top * sizeof(real), m, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < m * n_top; i++) outp_ix[u0 * n_top + i] = (IX)h_ids[i];
+            if (outp_score) memcpy(outp_score + u0 * n_top, h_sc.data(), m * n_top * sizeof(real));
+        }
+        return 0;
+    };
+    const int rc = body();
+    cudaFree(dB); cudaFree(dA); cudaFree(dAsel); cudaFree(sc_in); cudaFree(sc_out); cudaFree(id_in);
+    cudaFree(id_out); cudaFree(seg); cudaFree(dusers); cudaFree(dexp); cudaFree(dexi); cudaFree(tmp);
+    return rc;
+}
+
+template <class real, class IX>
+static int topn_single_impl(const real* a_vec, const real* B, int k, const IX* include_ix, size_t n_include,
+                            IX* exclude_ix, size_t n_exclude, IX* outp_ix, real* outp_score, size_t n_top, size_t n)
+{
+    // argument checks of src/topN.c:121-128
+    if (n_include == 0) include_ix = nullptr;
+    if (n_exclude == 0) exclude_ix = nullptr;
+    if (include_ix && exclude_ix) return 2;
+    if (n_top == 0) return 2;
+    if (n_exclude > n - n_top) return 2;
+    if (n_include > n) return 2;
+    if (include_ix) {
+        // score only the listed items: gather them into a dense candidate matrix
+        if (n_top > n_include) return 2;
+        std::vector<real> cand(n_include * (size_t)k);
+        for (size_t t = 0; t < n_include; t++)
+            memcpy(&cand[t * k], B + (size_t)include_ix[t] * k, (size_t)k * sizeof(real));
+        std::vector<IX> pos(n_top);
+        int rc = topn_batch_impl<real, IX>(a_vec, cand.data(), k, nullptr, 1, 1, nullptr, nullptr, pos.data(),
+                                           outp_score, n_top, n_include, true);
+        if (rc) return rc;
+        for (size_t t = 0; t < n_top; t++) outp_ix[t] = include_ix[(size_t)pos[t]];
+        return 0;
+    }
+    if (exclude_ix) {
+        // the reference sorts the caller's exclusion list in place (src/topN.c:159-160)
+        std::sort(exclude_ix, exclude_ix + n_exclude);
+        IX ptr[2] = {0, (IX)n_exclude};
+        return topn_batch_impl<real, IX>(a_vec, B, k, nullptr, 1, 1, ptr, exclude_ix, outp_ix, outp_score, n_top, n, true);
+    }
+    return topn_batch_impl<real, IX>(a_vec, B, k, nullptr, 1, 1, nullptr, nullptr, outp_ix, outp_score, n_top, n, true);
+}
+
+extern "C" int pmf_b200_topN(int dtype, int index_bytes, const void* a_vec, const void* B, int k,
+                             const void* include_ix, size_t n_include, const void* exclude_ix, size_t n_exclude,
+                             void* outp_ix, void* outp_score, size_t n_top, size_t n)
+{
+    if (pmf_b200_device_count() <= 0) return fail("no usable CUDA device: poismf_b200 has no CPU fallback");
+    if (dtype == PMF_F32 && index_bytes == 8) return topn_single_impl((const float*)a_vec, (const float*)B, k, (const uint64_t*)include_ix, n_include, (uint64_t*)exclude_ix, n_exclude, (uint64_t*)outp_ix, (float*)outp_score, n_top, n);
+    if (dtype == PMF_F32 && index_bytes == 4) return topn_single_impl((const float*)a_vec, (const float*)B, k, (const int*)include_ix, n_include, (int*)exclude_ix, n_exclude, (int*)outp_ix, (float*)outp_score, n_top, n);
+    if (dtype == PMF_F64 && index_bytes == 8) return topn_single_impl((const double*)a_vec, (const double*)B, k, (const uint64_t*)include_ix, n_include, (uint64_t*)exclude_ix, n_exclude, (uint64_t*)outp_ix, (double*)outp_score, n_top, n);
+    if (dtype == PMF_F64 && index_bytes == 4) return topn_single_impl((const double*)a_vec, (const double*)B, k, (const int*)include_ix, n_include, (int*)exclude_ix, n_exclude, (int*)outp_ix, (double*)outp_score, n_top, n);
+    return fail("topN: bad dtype/index width");
+}
+
+extern "C" int pmf_b200_topN_batch(int dtype, int index_bytes, const void* A, const void* B, int k,
+                                   const void* user_ix, size_t n_users, size_t dimA,
+                                   const void* excl_ptr, const void* excl_ix,
+                                   void* outp_ix, void* outp_score, size_t n_top, size_t n)
+{
+    if (pmf_b200_device_count() <= 0) return fail("no usable CUDA device: poismf_b200 has no CPU fallback");
+    if (dtype == PMF_F32 && index_bytes == 8) return topn_batch_impl((const float*)A, (const float*)B, k, (const uint64_t*)user_ix, n_users, dimA, (const uint64_t*)excl_ptr, (const uint64_t*)excl_ix, (uint64_t*)outp_ix, (float*)outp_score, n_top, n, false);
+    if (dtype == PMF_F32 && index_bytes == 4) return topn_batch_impl((const float*)A, (const float*)B, k, (const int*)user_ix, n_users, dimA, (const int*)excl_ptr, (const int*)excl_ix, (int*)outp_ix, (float*)outp_score, n_top, n, false);
+    if (dtype == PMF_F64 && index_bytes == 8) return topn_batch_impl((const double*)A, (const double*)B, k, (const uint64_t*)user_ix, n_users, dimA, (const uint64_t*)excl_ptr, (const uint64_t*)excl_ix, (uint64_t*)outp_ix, (double*)outp_score, n_top, n, false);
+    if (dtype == PMF_F64 && index_bytes == 4) return topn_batch_impl((const double*)A, (const double*)B, k, (const int*)user_ix, n_users, dimA, (const int*)excl_ptr, (const int*)excl_ix, (int*)outp_ix, (double*)outp_score, n_top, n, false);
+    return fail("topN_batch: bad dtype/index width");
+}

@@ -1,0 +1,141 @@
+// poismf_b200 — half-sweep kernels: one warp per short row, one CTA per heavy row.
+//
+// Replaces the OpenMP `parallel for schedule(dynamic)` row loops of the reference
+// (/root/reference/src/poismf.c:159-187 pg, :296-321 cg, :352-397 tncg).
+// Rows are binned by non-zero count on the host (plan.cpp); each bin is one launch
+// of a persistent grid whose teams fetch rows from a list sorted by decreasing
+// length (longest-processing-time-first) through an atomic counter.
+#pragma once
+#include "solver_pg_cg.cuh"
+#include "solver_tn.cuh"
+
+namespace pmf {
+
+template <class real> struct SideParams {
+    real* M;               // factors being updated  [dim   x ldf]
+    const real* F;         // fixed factors          [other x ldf]
+    const real* xv;        // non-zero values of this side's compressed matrix
+    const long long* ptr;  // row pointers (CSR for the A side, CSC for the B side)
+    const int* ind;        // indices into F
+    const real* csum;      // prepared column sums of F (+l1, pg: pre-scaled)
+    const int* rows;       // rows of this launch, longest first
+    int nrows;
+    int* counter;          // dynamic fetch counter (zeroed before the launch)
+    int k, kp, ldf;
+    int cap;               // tile capacity (non-zeros) of a team's shared slice; 0: tile stays in global
+    int slice_bytes;       // shared bytes per team
+    HalfSweepConsts<real> hc;
+    real* gscratch;        // per-CTA global scratch for rows that are not staged (3*gs_stride reals)
+    long long gs_stride;
+    unsigned long long* n_unchanged;  // tncg early-stop counter (src/poismf.c:393-396)
+};
+
+PMF_DEVINL int num_vecs(int method)
+{
+    return method == M_PG ? 3 : (method == M_CG ? 7 : TN_NUM_VECS);
+}
+
+// Shared-memory slice of one team:
+//   [team scratch 288 B][gscr team*16 B][vectors NV*kp][xv,pa,pb,pc: 4*cap][tile cap*kp]
+template <class real> struct Slice {
+    void* team_scratch;
+    real* gscr;
+    real* vecs;
+    real *xv, *pa, *pb, *pc;
+    real* tile;
+    PMF_DEVINL Slice(unsigned char* base, int team_size, int nvec, int kp, int cap)
+    {
+        team_scratch = base; base += 288;
+        gscr = (real*)base; base += (size_t)team_size * 16;
+        vecs = (real*)base; base += (size_t)nvec * kp * sizeof(real);
+        xv = (real*)base; pa = xv + cap; pb = pa + cap; pc = pb + cap;
+        base += (size_t)4 * cap * sizeof(real);
+        tile = (real*)base;
+    }
+};
+
+template <class real, int METHOD, bool STRICT, bool CACHED, class Team>
+PMF_DEVINL void process_row(const Team& tm, const SideParams<real>& P, const Slice<real>& S,
+                            int row, real* gscratch_cta)
+{
+    const long long beg = P.ptr[row];
+    const int n = (int)(P.ptr[row + 1] - beg);
+    const int k = P.k, kp = P.kp;
+    RowView<real> rv;
+    rv.F = P.F; rv.ind = P.ind + beg; rv.n = n; rv.k = k; rv.kp = kp; rv.ldf = P.ldf;
+    rv.gscr = S.gscr;
+    const int nvec = num_vecs(METHOD);
+    // zero every vector (pads must be 0 and finite for the 16-byte dot loops)
+    for (int i = tm.rank(); i < nvec * kp; i += tm.size()) S.vecs[i] = (real)0;
+    if (P.cap > 0 && n <= P.cap) {
+        rv.tile = S.tile; rv.xv = S.xv; rv.pa = S.pa; rv.pb = S.pb; rv.pc = S.pc;
+        stage_tile(tm, P.F, rv.ind, P.xv + beg, n, P.ldf, kp, S.tile, S.xv);
+    } else {
+        rv.tile = nullptr; rv.xv = P.xv + beg;
+        rv.pa = gscratch_cta; rv.pb = gscratch_cta + P.gs_stride; rv.pc = gscratch_cta + 2 * P.gs_stride;
+        tm.sync();
+    }
+    real* V = S.vecs;
+    real* x = V;                  // vector 0: the row being solved
+    real* csum = V + kp;          // vector 1: column sums for this row
+    real* Mrow = P.M + (size_t)row * P.ldf;
+    for (int i = tm.rank(); i < k; i += tm.size()) x[i] = Mrow[i];
+    if (P.hc.w == (real)1) {
+        for (int i = tm.rank(); i < k; i += tm.size()) csum[i] = P.csum[i];
+        tm.sync();
+    } else {
+        tm.sync();
+        weighted_colsum<STRICT>(tm, rv, P.csum, P.hc, rv.pb, csum);
+    }
+
+    if (METHOD == M_PG) {
+        solve_pg<STRICT>(tm, rv, P.hc, x, csum, V + 2 * kp);
+    } else if (METHOD == M_CG) {
+        CgVecs<real> vv;
+        vv.x = x; vv.csum = csum;
+        vv.g0 = V + 2 * kp; vv.g1 = V + 3 * kp; vv.d0 = V + 4 * kp; vv.d1 = V + 5 * kp; vv.xnew = V + 6 * kp;
+        if (CACHED && P.hc.limit_step) solve_cg<STRICT, true>(tm, rv, P.hc, vv);
+        else solve_cg<STRICT, false>(tm, rv, P.hc, vv);
+    } else {
+        solve_tn<STRICT>(tm, rv, P.hc, V, Mrow, P.n_unchanged);
+    }
+    tm.sync();
+    for (int i = tm.rank(); i < k; i += tm.size()) Mrow[i] = x[i];
+    tm.sync();
+}
+
+template <class real, int METHOD, bool STRICT, bool CACHED>
+__global__ void __launch_bounds__(256) rows_warp_kernel(const SideParams<real> P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5;
+    Slice<real> S(smem + (size_t)warp * P.slice_bytes, 32, num_vecs(METHOD), P.kp, P.cap);
+    WarpTeam tm(S.team_scratch);
+    for (;;) {
+        int idx = 0;
+        if (tm.lane == 0) idx = atomicAdd(P.counter, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= P.nrows) break;
+        process_row<real, METHOD, STRICT, CACHED>(tm, P, S, P.rows[idx], (real*)nullptr);
+    }
+}
+
+template <class real, int METHOD, bool STRICT, bool CACHED>
+__global__ void __launch_bounds__(256) rows_block_kernel(const SideParams<real> P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int next_row;
+    Slice<real> S(smem, blockDim.x, num_vecs(METHOD), P.kp, P.cap);
+    BlockTeam tm(S.team_scratch);
+    real* gs = P.gscratch ? P.gscratch + (size_t)blockIdx.x * 3 * P.gs_stride : nullptr;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_row = atomicAdd(P.counter, 1);
+        __syncthreads();
+        const int idx = next_row;
+        if (idx >= P.nrows) break;
+        process_row<real, METHOD, STRICT, CACHED>(tm, P, S, P.rows[idx], gs);
+    }
+}
+
+}  // namespace pmf

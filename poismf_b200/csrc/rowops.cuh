@@ -1,0 +1,315 @@
+// poismf_b200 — per-row evaluation primitives.
+//
+// A row's sub-problem touches the gathered rows {F[j] : j in the row's non-zeros}
+// ("tile") many times (once per objective/gradient evaluation).  The tile is
+// staged ONCE per half-sweep into shared memory with 16-byte cp.async copies
+// (row stride `kp` chosen so that 16-byte accesses by consecutive lanes to
+// consecutive tile rows are bank-conflict free), and every evaluation then runs
+// out of shared memory:
+//   dots  : one lane per non-zero, sequential over the k components
+//           (== the reference's cblas_tdot per non-zero, src/poismf.c:204,219,259)
+//   gaxpy : one lane per 16-byte component chunk, sequential over the non-zeros
+//           (== the reference's chain of cblas_taxpy into grad, :218-221,:260-261)
+// Rows whose tile does not fit the team's shared-memory slice run the same code
+// reading the factor rows straight from global memory / L2 (tile == nullptr).
+#pragma once
+#include "common.cuh"
+
+namespace pmf {
+
+template <class real> struct Vec16;
+template <> struct Vec16<float> { using type = float4; };
+template <> struct Vec16<double> { using type = double2; };
+
+PMF_DEVINL float vdot4(const float4& a, const float4& b, float s)
+{
+    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    return s;
+}
+PMF_DEVINL double vdot4(const double2& a, const double2& b, double s)
+{
+    s = fma(a.x, b.x, s); s = fma(a.y, b.y, s);
+    return s;
+}
+PMF_DEVINL void vfma(float4& acc, float c, const float4& b)
+{
+    acc.x = fmaf(c, b.x, acc.x); acc.y = fmaf(c, b.y, acc.y);
+    acc.z = fmaf(c, b.z, acc.z); acc.w = fmaf(c, b.w, acc.w);
+}
+PMF_DEVINL void vfma(double2& acc, double c, const double2& b)
+{
+    acc.x = fma(c, b.x, acc.x); acc.y = fma(c, b.y, acc.y);
+}
+PMF_DEVINL void vzero(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+PMF_DEVINL void vzero(double2& v) { v = make_double2(0., 0.); }
+PMF_DEVINL void vaddto(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+PMF_DEVINL void vaddto(double2& a, const double2& b) { a.x += b.x; a.y += b.y; }
+
+PMF_DEVINL void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+PMF_DEVINL void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Everything a team needs to know about the row it is working on.
+template <class real> struct RowView {
+    const real* tile;  // staged tile in shared memory (row stride kp) or nullptr
+    const real* F;     // fixed factor matrix in global memory (row stride ldf, pads are 0)
+    const int* ind;    // the row's non-zero indices (global)
+    const real* xv;    // the row's non-zero values (shared copy when staged, else global)
+    real* pa;          // per-non-zero scratch: <x, F_j> at the current point
+    real* pb;          // per-non-zero scratch: coefficients / terms
+    real* pc;          // per-non-zero scratch: <x_trial, F_j>
+    real* gscr;        // team-size * 16 bytes of reduction scratch (fast gaxpy)
+    int n;             // non-zeros in this row
+    int k, kp, ldf;    // components; tile stride; global stride (multiple of 16 bytes)
+    PMF_DEVINL const real* rowp(int t) const
+    {
+        return tile ? tile + (size_t)t * kp : F + (size_t)ind[t] * ldf;
+    }
+};
+
+// Gather the row's tile (and its values) into shared memory.
+template <class real, class Team>
+PMF_DEVINL void stage_tile(const Team& tm, const real* __restrict__ F, const int* __restrict__ ind,
+                           const real* __restrict__ xv_g, int n, int ldf, int kp,
+                           real* tile, real* xv_s)
+{
+    constexpr int V = RealTraits<real>::V;
+    const int L = ldf / V;  // 16-byte chunks per factor row
+    const int total = n * L;
+    for (int idx = tm.rank(); idx < total; idx += tm.size()) {
+        const int t = idx / L, c = idx - t * L;
+        cp_async16(tile + (size_t)t * kp + c * V, F + (size_t)ind[t] * ldf + c * V);
+    }
+    for (int t = tm.rank(); t < n; t += tm.size()) xv_s[t] = xv_g[t];
+    cp_async_wait_all();
+    tm.sync();
+}
+
+// out[t] = <a, F_t>  for every non-zero t of the row.  `a` is a shared-memory
+// vector of kp reals whose pads [k, kp) are zero.
+template <bool STRICT, class real, class Team>
+PMF_DEVINL void dots(const Team& tm, const RowView<real>& rv, const real* a, real* out)
+{
+    const int n = rv.n;
+    if (STRICT) {
+        const int k = rv.k;
+        for (int t = tm.rank(); t < n; t += tm.size()) {
+            const real* r = rv.rowp(t);
+            real s = 0;
+            for (int i = 0; i < k; i++) s = add_rn(s, mul_rn(a[i], r[i]));
+            out[t] = s;
+        }
+    } else {
+        using VT = typename Vec16<real>::type;
+        constexpr int V = RealTraits<real>::V;
+        const int nv = rv.ldf / V;
+        const VT* av = reinterpret_cast<const VT*>(a);
+        const int sz = tm.size();
+        for (int t = tm.rank(); t < n; t += 4 * sz) {
+            // four non-zeros per lane share each load of `a`
+            const int t1 = t + sz, t2 = t + 2 * sz, t3 = t + 3 * sz;
+            const VT* r0 = reinterpret_cast<const VT*>(rv.rowp(t));
+            const VT* r1 = t1 < n ? reinterpret_cast<const VT*>(rv.rowp(t1)) : r0;
+            const VT* r2 = t2 < n ? reinterpret_cast<const VT*>(rv.rowp(t2)) : r0;
+            const VT* r3 = t3 < n ? reinterpret_cast<const VT*>(rv.rowp(t3)) : r0;
+            real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 2
+            for (int c = 0; c < nv; c++) {
+                const VT x = av[c];
+                s0 = vdot4(x, r0[c], s0);
+                s1 = vdot4(x, r1[c], s1);
+                s2 = vdot4(x, r2[c], s2);
+                s3 = vdot4(x, r3[c], s3);
+            }
+            out[t] = s0;
+            if (t1 < n) out[t1] = s1;
+            if (t2 < n) out[t2] = s2;
+            if (t3 < n) out[t3] = s3;
+        }
+    }
+    tm.sync();
+}
+
+// g[i] (+)= sum_t coef[t] * F_t[i].
+//   STRICT: g[i] is accumulated in place, t ascending, two roundings per term
+//           (exactly the reference's chain of axpy calls on `grad`).
+//   fast  : partial sums per thread group, then g[i] = g[i] + total.
+// `g` is a shared vector of kp reals.  Ends with a team sync.
+template <bool STRICT, class real, class Team>
+PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef, real* g)
+{
+    const int n = rv.n;
+    if (STRICT) {
+        const int k = rv.k;
+        for (int i = tm.rank(); i < k; i += tm.size()) {
+            real acc = g[i];
+            for (int t = 0; t < n; t++) acc = add_rn(acc, mul_rn(coef[t], rv.rowp(t)[i]));
+            g[i] = acc;
+        }
+        tm.sync();
+        return;
+    }
+    using VT = typename Vec16<real>::type;
+    constexpr int V = RealTraits<real>::V;
+    const int L = rv.ldf / V;
+    const int sz = tm.size(), rk = tm.rank();
+    VT* scr = reinterpret_cast<VT*>(rv.gscr);
+    VT* gv = reinterpret_cast<VT*>(g);
+    if (L <= sz) {
+        const int groups = sz / L;
+        const int grp = rk / L, c = rk - grp * L;
+        VT acc0, acc1;
+        vzero(acc0); vzero(acc1);
+        if (grp < groups) {
+            int t = grp;
+            for (; t + groups < n; t += 2 * groups) {
+                const VT b0 = reinterpret_cast<const VT*>(rv.rowp(t))[c];
+                const VT b1 = reinterpret_cast<const VT*>(rv.rowp(t + groups))[c];
+                vfma(acc0, coef[t], b0);
+                vfma(acc1, coef[t + groups], b1);
+            }
+            if (t < n) vfma(acc0, coef[t], reinterpret_cast<const VT*>(rv.rowp(t))[c]);
+            vaddto(acc0, acc1);
+        }
+        scr[rk] = acc0;
+        tm.sync();
+        if (rk < L) {  // group 0 folds the other groups in a fixed order
+            VT tot = scr[rk];
+            for (int gq = 1; gq < groups; gq++) vaddto(tot, scr[gq * L + rk]);
+            VT base = gv[rk];
+            vaddto(base, tot);
+            gv[rk] = base;
+        }
+    } else {
+        for (int c = rk; c < L; c += sz) {
+            VT acc;
+            vzero(acc);
+            for (int t = 0; t < n; t++) vfma(acc, coef[t], reinterpret_cast<const VT*>(rv.rowp(t))[c]);
+            VT base = gv[c];
+            vaddto(base, acc);
+            gv[c] = base;
+        }
+    }
+    tm.sync();
+    // keep pads at zero (F pads are zero, so this is already the case; be explicit)
+}
+
+// Sequential sum over the non-zeros of  x_t * log(p_t)  (the `lsum` of
+// src/poismf.c:200-206,255-263).  Every member gets the same value.
+template <bool STRICT, class real, class Team>
+PMF_DEVINL real sum_xlogp(const Team& tm, const RowView<real>& rv, const real* p)
+{
+    const int n = rv.n;
+    if (STRICT) {
+        real s = 0;
+        if (tm.rank() == 0)
+            for (int t = 0; t < n; t++) s = xlogp_acc<true>(s, rv.xv[t], p[t]);
+        return tm.bcast0(s);
+    }
+    real s = 0;
+    for (int t = tm.rank(); t < n; t += tm.size()) s += xlogp(rv.xv[t], p[t]);
+    return tm.sum(s);
+}
+
+// Constants of one half-sweep's row sub-problems.
+template <class real> struct HalfSweepConsts {
+    real l2;        // l2_reg
+    real two_l2;    // (real)(2. * l2_reg): the axpy alpha of src/poismf.c:215,239,269
+    real w;         // w_mult
+    real wm1;       // (real)(w_mult - 1.)  src/poismf.c:113
+    real step_w;    // pg: step_size * w_mult      (:151)
+    real neg_step;  // pg: -step_size              (:460,:533)
+    real cdiv;      // pg: 1/(1+2*l2*step)         (:511)
+    int maxupd;
+    int limit_step, reuse_prev, early_stop;
+    int method;
+};
+
+// csum_row = (w-1) * sum_t F_t + csum  [* neg_step for pg]   (adjustment_Bsum, :85-123;
+// pg scaling :526,:576).  Only when w != 1.
+template <bool STRICT, class real, class Team>
+PMF_DEVINL void weighted_colsum(const Team& tm, const RowView<real>& rv, const real* csum,
+                                const HalfSweepConsts<real>& hc, real* ones, real* out)
+{
+    const int k = rv.k;
+    for (int t = tm.rank(); t < rv.n; t += tm.size()) ones[t] = (real)1;
+    vfill(tm, out, (real)0, rv.kp);
+    tm.sync();
+    gaxpy<STRICT>(tm, rv, ones, out);
+    for (int i = tm.rank(); i < k; i += tm.size()) {
+        real v = mul<STRICT>(out[i], hc.wm1);
+        v = add<STRICT>(v, csum[i]);
+        if (hc.method == M_PG) v = mul<STRICT>(v, hc.neg_step);
+        out[i] = v;
+    }
+    tm.sync();
+}
+
+// f = <csum,x> + l2<x,x> - w * sum x_t log<x,F_t>      (calc_fun_single, :194-208)
+// Leaves <x,F_t> in `pout`.
+template <bool STRICT, class real, class Team>
+PMF_DEVINL real eval_f_cg(const Team& tm, const RowView<real>& rv, const real* csum,
+                          const HalfSweepConsts<real>& hc, const real* x, real* pout)
+{
+    dots<STRICT>(tm, rv, x, pout);
+    real reg = vdot<STRICT>(tm, csum, x, rv.k);
+    reg = mad<STRICT>(hc.l2, vdot<STRICT>(tm, x, x, rv.k), reg);
+    const real ls = sum_xlogp<STRICT>(tm, rv, pout);
+    return sub<STRICT>(reg, mul<STRICT>(ls, hc.w));
+}
+
+// grad = csum + 2 l2 x - w * sum (x_t/<x,F_t>) F_t     (calc_grad_single[_w], :210-240)
+// `p` must hold <x,F_t>.  Uses rv.pb for the coefficients.
+template <bool STRICT, class real, class Team>
+PMF_DEVINL void eval_g_cg(const Team& tm, const RowView<real>& rv, const real* csum,
+                          const HalfSweepConsts<real>& hc, const real* x, const real* p, real* g)
+{
+    const int k = rv.k;
+    for (int t = tm.rank(); t < rv.n; t += tm.size()) rv.pb[t] = -rv.xv[t] / p[t];
+    if (hc.w == (real)1) {
+        for (int i = tm.rank(); i < k; i += tm.size()) g[i] = mad<STRICT>(hc.two_l2, x[i], csum[i]);
+        tm.sync();
+        gaxpy<STRICT>(tm, rv, rv.pb, g);
+    } else {
+        vfill(tm, g, (real)0, k);
+        tm.sync();
+        gaxpy<STRICT>(tm, rv, rv.pb, g);
+        for (int i = tm.rank(); i < k; i += tm.size()) {
+            real v = mul<STRICT>(g[i], hc.w);
+            v = add<STRICT>(v, csum[i]);
+            g[i] = mad<STRICT>(hc.two_l2, x[i], v);
+        }
+        tm.sync();
+    }
+}
+
+// f (WITHOUT the l2 term, Q3) and grad in one go      (calc_fun_and_grad, :242-273)
+template <bool STRICT, class real, class Team>
+PMF_DEVINL real eval_fg_tn(const Team& tm, const RowView<real>& rv, const real* csum,
+                           const HalfSweepConsts<real>& hc, const real* x, real* g)
+{
+    const int k = rv.k;
+    dots<STRICT>(tm, rv, x, rv.pa);
+    for (int t = tm.rank(); t < rv.n; t += tm.size()) rv.pb[t] = -rv.xv[t] / rv.pa[t];
+    vfill(tm, g, (real)0, k);
+    tm.sync();
+    gaxpy<STRICT>(tm, rv, rv.pb, g);
+    const real ls = sum_xlogp<STRICT>(tm, rv, rv.pa);
+    const real reg = vdot<STRICT>(tm, csum, x, k);
+    for (int i = tm.rank(); i < k; i += tm.size()) {
+        real v = g[i];
+        if (hc.w != (real)1) v = mul<STRICT>(v, hc.w);
+        v = add<STRICT>(v, csum[i]);
+        g[i] = mad<STRICT>(hc.two_l2, x[i], v);
+    }
+    tm.sync();
+    return sub<STRICT>(reg, mul<STRICT>(ls, hc.w));
+}
+
+}  // namespace pmf

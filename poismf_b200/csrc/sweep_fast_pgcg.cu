@@ -1,0 +1,3 @@
+#define PMF_INST_STRICT 0
+#define PMF_INST_TN 0
+#include "sweep_inst.cuh"

@@ -1,0 +1,3 @@
+#define PMF_INST_STRICT 1
+#define PMF_INST_TN 1
+#include "sweep_inst.cuh"

@@ -1,0 +1,79 @@
+"""Device-resident fit: the handle API of include/poismf_b200.h from Python.
+
+`DeviceFit` keeps the factors and both orientations of the count matrix in HBM
+between sweeps; this is what bench.py times as the kernel-level figure, and what
+the sharding layer drives half-sweep by half-sweep.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class DeviceFit:
+    def __init__(self, dimA, dimB, k, dtype=np.float32, device=0):
+        _lib.require_gpu()
+        self.L = _lib.lib()
+        self.dtype = np.dtype(dtype)
+        self.dimA, self.dimB, self.k = int(dimA), int(dimB), int(k)
+        self.h = self.L.pmf_b200_create(_lib.dtype_code(dtype), self.dimA, self.dimB, self.k, int(device))
+        if not self.h:
+            raise MemoryError(_lib.last_error())
+        self.ldf = self.L.pmf_b200_ldf(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pmf_b200_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc == 1:
+            raise MemoryError(_lib.last_error())
+        return rc
+
+    def set_matrix(self, side, values, indptr, indices, row_begin=0, n_rows=None):
+        n_rows = (indptr.shape[0] - 1) if n_rows is None else n_rows
+        assert values.dtype == self.dtype and values.flags.c_contiguous
+        self._ck(self.L.pmf_b200_set_matrix(self.h, side, _lib.ptr(values), _lib.ptr(indptr), _lib.ptr(indices),
+                                            values.shape[0], _lib.index_bytes(indptr), row_begin, n_rows))
+
+    def set_csr_csc(self, csr, csc):
+        self.set_matrix(_lib.SIDE_CSR, *csr)
+        self.set_matrix(_lib.SIDE_CSC, *csc)
+
+    def set_factors(self, A=None, B=None):
+        for M in (A, B):
+            assert M is None or (M.dtype == self.dtype and M.flags.c_contiguous)
+        self._ck(self.L.pmf_b200_set_factors(self.h, _lib.ptr(A), _lib.ptr(B)))
+
+    def get_factors(self, A=None, B=None):
+        A = np.empty((self.dimA, self.k), self.dtype) if A is None else A
+        B = np.empty((self.dimB, self.k), self.dtype) if B is None else B
+        self._ck(self.L.pmf_b200_get_factors(self.h, _lib.ptr(A), _lib.ptr(B)))
+        return A, B
+
+    def bind_factors(self, A_dev_ptr=None, B_dev_ptr=None):
+        self._ck(self.L.pmf_b200_bind_factors(self.h, A_dev_ptr, B_dev_ptr))
+
+    def factor_ptr(self, which):
+        return self.L.pmf_b200_factor_ptr(self.h, which)
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.L.pmf_b200_set_stream(self.h, stream_ptr))
+
+    def sweeps(self, params):
+        return self._ck(self.L.pmf_b200_sweeps(self.h, C.byref(params)))
+
+    def half_sweep(self, side, params, step_size, cnst_div):
+        n = C.c_ulonglong(0)
+        self._ck(self.L.pmf_b200_half_sweep(self.h, side, C.byref(params), float(step_size), float(cnst_div),
+                                            C.byref(n)))
+        return n.value
+
+    def sync(self):
+        self._ck(self.L.pmf_b200_sync(self.h))
