@@ -87,6 +87,20 @@ int pmf_b200_half_sweep(pmf_b200_handle* h, int side, const pmf_b200_params* p, 
                         double cnst_div, unsigned long long* n_unchanged);
 int pmf_b200_sync(pmf_b200_handle* h);
 
+/* Per-launch device timing of the row kernels (CUDA events on the handle's stream),
+ * for bench.py's roofline line: one entry per (side, row bin). */
+typedef struct pmf_b200_bin_profile {
+    int side;                  /* PMF_SIDE_CSR / PMF_SIDE_CSC */
+    int block_team;            /* 0: warp per row, 1: CTA per row */
+    int cap;                   /* staged tile capacity (0: tile read from global memory) */
+    int nrows;                 /* rows in the bin */
+    unsigned long long nnz;    /* non-zeros in the bin */
+    unsigned long long launches;
+    double ms;                 /* summed device time of those launches */
+} pmf_b200_bin_profile;
+int pmf_b200_set_profiling(pmf_b200_handle* h, int on);                       /* also clears the counters */
+int pmf_b200_get_profile(pmf_b200_handle* h, pmf_b200_bin_profile* out, int max_entries);  /* returns #entries */
+
 /* ---- drop-in entry points (host pointers in, host pointers out) ---------- */
 /* Replaces run_poismf, src/poismf.c:435-632 (prototype src/poismf.h:226-233). */
 int pmf_b200_run_poismf(int dtype, int index_bytes,

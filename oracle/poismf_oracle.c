@@ -1035,6 +1035,38 @@ int oracle_run_poismf(real *A, const real *Xr, const ix_t *Xr_indptr, const ix_t
     return 0;
 }
 
+
+/* One half-sweep in isolation (what the sharding layer drives): update every row of M
+ * with F fixed, including the column-sum preparation of src/poismf.c:511-526 (B side,
+ * is_A_side=0) or :562-577 (A side, is_A_side=1: pg scales the sums twice, Q1).
+ * `step_size` is the CURRENT pg step (already halved for the A side by the caller). */
+int oracle_half_sweep(int method, real *M, const real *F, const real *xv, const ix_t *ptr,
+                      const ix_t *ind, size_t dim, size_t other, size_t k,
+                      real l2_reg, real l1_reg, real w_mult, real step_size, int is_A_side,
+                      size_t maxupd, int limit_step, int reuse_prev)
+{
+    real *csum = (real *)malloc(sizeof(real) * k);
+    real *buf = (real *)malloc(sizeof(real) * 22 * k);
+    int *ibuf = (int *)malloc(sizeof(int) * k);
+    real *csum_w = (w_mult != 1.) ? (real *)malloc(sizeof(real) * k * dim) : NULL;
+    real neg_step = -step_size;
+    /* cnst_div uses the step of the START of the sweep (:511): un-halve it on the A side */
+    real step0 = (method == 3 && is_A_side) ? (real)(step_size * 2.) : step_size;
+    real cdiv = 1. / (1. + 2. * l2_reg * step0);
+    colsum(csum, F, other, k);
+    if (l1_reg > 0.) for (size_t c = 0; c < k; c++) csum[c] += l1_reg;
+    if (w_mult != 1.) weighted_sums(F, csum, csum_w, ind, ptr, dim, k, w_mult);
+    if (method == 3) {
+        if (w_mult == 1.) vscal((int)k, neg_step, csum);
+        else for (size_t i = 0; i < dim * k; i++) csum_w[i] *= neg_step;
+        if (is_A_side) vscal((int)k, neg_step, csum);
+    }
+    half_sweep(method, M, F, xv, ptr, ind, dim, k, csum, csum_w, l2_reg, w_mult, step_size, cdiv,
+               maxupd, limit_step, reuse_prev, 0, buf, ibuf);
+    free(csum); free(buf); free(ibuf); free(csum_w);
+    return 0;
+}
+
 /* Single-row entry points for known-answer tests (cg / tncg solvers alone). */
 void oracle_cg_row(real *a, const real *F, const real *csum, const real *xval,
                    const ix_t *xind, ix_t nnz, int k, real l2, real w,

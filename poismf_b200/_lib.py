@@ -24,6 +24,7 @@ SYMBOLS = [
     "pmf_b200_create", "pmf_b200_destroy", "pmf_b200_ldf", "pmf_b200_set_matrix",
     "pmf_b200_set_factors", "pmf_b200_get_factors", "pmf_b200_bind_factors", "pmf_b200_factor_ptr",
     "pmf_b200_set_stream", "pmf_b200_sweeps", "pmf_b200_half_sweep", "pmf_b200_sync",
+    "pmf_b200_set_profiling", "pmf_b200_get_profile",
     "pmf_b200_run_poismf", "pmf_b200_predict_multiple", "pmf_b200_topN", "pmf_b200_topN_batch",
 ]
 
@@ -33,6 +34,11 @@ class Params(C.Structure):
                 ("step_size", C.c_double), ("method", C.c_int), ("limit_step", C.c_int),
                 ("numiter", C.c_size_t), ("maxupd", C.c_size_t), ("early_stop", C.c_int),
                 ("reuse_prev", C.c_int), ("flags", C.c_int)]
+
+
+class BinProfile(C.Structure):
+    _fields_ = [("side", C.c_int), ("block_team", C.c_int), ("cap", C.c_int), ("nrows", C.c_int),
+                ("nnz", C.c_ulonglong), ("launches", C.c_ulonglong), ("ms", C.c_double)]
 
 
 _lib = None
@@ -65,6 +71,8 @@ def lib():
     L.pmf_b200_sweeps.argtypes = [vp, C.POINTER(Params)]
     L.pmf_b200_half_sweep.argtypes = [vp, i, C.POINTER(Params), d, d, C.POINTER(C.c_ulonglong)]
     L.pmf_b200_sync.argtypes = [vp]
+    L.pmf_b200_set_profiling.argtypes = [vp, i]
+    L.pmf_b200_get_profile.argtypes = [vp, C.POINTER(BinProfile), i]
     L.pmf_b200_run_poismf.argtypes = [i, i] + [vp] * 8 + [sz, sz, sz, d, d, d, d, i, i, sz, sz, i, i, i, i]
     L.pmf_b200_predict_multiple.argtypes = [i, i, vp, vp, vp, vp, vp, sz, i, sz, sz]
     L.pmf_b200_topN.argtypes = [i, i, vp, vp, i, vp, sz, vp, sz, vp, vp, sz, sz]

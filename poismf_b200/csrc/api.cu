@@ -83,6 +83,8 @@ struct Bin {
     std::vector<int> rows;  // local row ids, longest first
     int* d_rows = nullptr;
     long long max_nnz = 0;
+    unsigned long long nnz = 0;
+    std::vector<cudaEvent_t> ev;   // profiling: start/stop pairs of this bin's launches
 };
 
 template <class real> struct Side {
@@ -101,6 +103,7 @@ template <class real> struct Side {
     int gs_ctas = 0;
     void free_plan()
     {
+        for (auto& b : bins) for (auto e : b.ev) cudaEventDestroy(e);
         if (d_all_rows) cudaFree(d_all_rows);
         if (gscratch) cudaFree(gscratch);
         d_all_rows = nullptr; gscratch = nullptr; d_empty = nullptr;
@@ -133,6 +136,9 @@ struct pmf_b200_handle {
     virtual int half_sweep(int side, const pmf_b200_params& p, double step, double cdiv,
                            unsigned long long* n_unchanged) = 0;
     virtual int sweeps(const pmf_b200_params& p) = 0;
+    virtual int get_profile(pmf_b200_bin_profile* out, int max_entries) = 0;
+    virtual void clear_profile() = 0;
+    bool profiling = false;
 };
 
 static const size_t SMEM_PER_SM = 233472;     // 228 KB
@@ -322,6 +328,7 @@ template <class real> struct HandleT : pmf_b200_handle {
             while (bi + 1 < bins.size() && n > bins[bi].cap) bi++;
             bins[bi].rows.push_back((int)r);
             bins[bi].max_nnz = std::max(bins[bi].max_nnz, n);
+            bins[bi].nnz += (unsigned long long)n;
         }
         size_t total = empty.size();
         for (auto& b : bins) {
@@ -444,18 +451,54 @@ template <class real> struct HandleT : pmf_b200_handle {
             cfg.max_grid = b.cap == 0 ? S.gs_ctas : (1 << 30);
             cfg.num_sms = num_sms;
             cudaError_t e;
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profiling) {
+                CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+                CK(cudaEventRecord(ev0, stream));
+            }
             if (p.method == PMF_TNCG)
                 e = strict ? launch_rows_tn_strict<real>(cfg, P) : launch_rows_tn_fast<real>(cfg, P);
             else
                 e = strict ? launch_rows_pgcg_strict<real>(cfg, P) : launch_rows_pgcg_fast<real>(cfg, P);
             LAUNCHED();
             if (e != cudaSuccess) return fail("row kernel launch failed: %s", cudaGetErrorString(e));
+            if (profiling) {
+                CK(cudaEventRecord(ev1, stream));
+                S.bins[bi].ev.push_back(ev0); S.bins[bi].ev.push_back(ev1);
+            }
         }
         if (hc.early_stop && n_unchanged) {
             CK(cudaMemcpyAsync(n_unchanged, d_unchanged, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
         }
         return 0;
+    }
+
+    void clear_profile() override
+    {
+        for (int sd = 0; sd < 2; sd++)
+            for (auto& b : sides[sd].bins) {
+                for (auto e : b.ev) cudaEventDestroy(e);
+                b.ev.clear();
+            }
+    }
+    int get_profile(pmf_b200_bin_profile* out, int max_entries) override
+    {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        int n = 0;
+        for (int sd = 0; sd < 2; sd++)
+            for (auto& b : sides[sd].bins) {
+                if (b.rows.empty() || n >= max_entries) continue;
+                pmf_b200_bin_profile& o = out[n++];
+                o.side = sd; o.block_team = b.block; o.cap = b.cap; o.nrows = (int)b.rows.size();
+                o.nnz = b.nnz; o.launches = b.ev.size() / 2; o.ms = 0;
+                for (size_t i = 0; i + 1 < b.ev.size(); i += 2) {
+                    float ms = 0;
+                    if (cudaEventElapsedTime(&ms, b.ev[i], b.ev[i + 1]) == cudaSuccess) o.ms += ms;
+                }
+            }
+        return n;
     }
 
     // ---- numiter alternating sweeps (src/poismf.c:506-608) -------------------------
@@ -532,6 +575,16 @@ extern "C" int pmf_b200_half_sweep(pmf_b200_handle* h, int side, const pmf_b200_
                                    double cnst_div, unsigned long long* n_unchanged)
 {
     return h->half_sweep(side, *p, step_size, cnst_div, n_unchanged);
+}
+extern "C" int pmf_b200_set_profiling(pmf_b200_handle* h, int on)
+{
+    h->clear_profile();
+    h->profiling = on != 0;
+    return 0;
+}
+extern "C" int pmf_b200_get_profile(pmf_b200_handle* h, pmf_b200_bin_profile* out, int max_entries)
+{
+    return h->get_profile(out, max_entries);
 }
 extern "C" int pmf_b200_sync(pmf_b200_handle* h)
 {

@@ -75,5 +75,14 @@ class DeviceFit:
                                             C.byref(n)))
         return n.value
 
+    def set_profiling(self, on=True):
+        self.L.pmf_b200_set_profiling(self.h, int(on))
+
+    def get_profile(self):
+        arr = (_lib.BinProfile * 64)()
+        n = self.L.pmf_b200_get_profile(self.h, arr, 64)
+        return [dict(side=a.side, block_team=a.block_team, cap=a.cap, nrows=a.nrows, nnz=a.nnz,
+                     launches=a.launches, ms=a.ms) for a in arr[:n]]
+
     def sync(self):
         self._ck(self.L.pmf_b200_sync(self.h))

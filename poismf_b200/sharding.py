@@ -1,0 +1,144 @@
+"""Row/column sharding of the alternating sweep across the GPUs of one box.
+
+The reference has no distributed code; its per-row updates within a half-sweep are
+independent (/root/reference/src/poismf.c:159-187, :296-321, :352-397: every row reads its
+own CSR/CSC slice, the FULL opposite factor matrix and the k column sums, and writes its
+own k numbers).  So:
+
+  * users are split into contiguous CSR row ranges balanced by non-zeros, items into
+    contiguous CSC column ranges balanced by non-zeros; rank r holds its two slices,
+  * A and B are replicated on every rank,
+  * after the B half-sweep every rank's freshly updated rows of B are exchanged
+    (one exchange step per half-sweep), likewise A after the A half-sweep,
+  * the column sums are recomputed locally from the replicated matrix (deterministic
+    order, no collective), and tncg's early-stop count is summed over ranks.
+
+One process per GPU (torchrun); torch.distributed is the plumbing (NCCL on GPUs, gloo in
+the CPU tests, where the row solver is stood in by a caller-supplied function).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def nnz_balanced_ranges(indptr, nparts):
+    """Split rows 0..n into `nparts` contiguous ranges with ~equal non-zeros.
+
+    Returns a list of (begin, end); ranges may be empty when nparts > rows."""
+    indptr = np.asarray(indptr).astype(np.int64)
+    n = indptr.shape[0] - 1
+    total = int(indptr[-1] - indptr[0])
+    cuts = [0]
+    for p in range(1, nparts):
+        target = indptr[0] + (total * p) // nparts
+        c = int(np.searchsorted(indptr, target, side="left"))
+        c = min(max(c, cuts[-1]), n)
+        cuts.append(c)
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(nparts)]
+
+
+def slice_compressed(mat, begin, end):
+    """Rows [begin, end) of a (values, indptr, indices) triple, indptr rebased to 0."""
+    vals, ptr, ind = mat
+    lo, hi = int(ptr[begin]), int(ptr[end])
+    return (np.ascontiguousarray(vals[lo:hi]),
+            np.ascontiguousarray(ptr[begin:end + 1] - ptr[begin]).astype(ptr.dtype),
+            np.ascontiguousarray(ind[lo:hi]))
+
+
+class ShardedSweep:
+    """Drives sharded alternating sweeps; mirrors run_poismf's outer loop (src/poismf.c:506-608).
+
+    backend: an object with
+        half_sweep(side, params, step, cnst_div) -> n_unchanged   (updates the LOCAL rows in place)
+        exchange(side)                                             (refresh the replicated matrix)
+    `GpuBackend` below is the product one; tests inject a CPU stand-in.
+    """
+
+    def __init__(self, backend, dimA, dimB, dtype, world_allreduce_int=None):
+        self.be = backend
+        self.dimA, self.dimB = dimA, dimB
+        self.dtype = np.dtype(dtype)
+        self.allreduce_int = world_allreduce_int or (lambda v: v)
+
+    def run(self, params):
+        from . import _lib
+        real = self.dtype.type
+        step = real(params.step_size)
+        l2 = real(params.l2_reg)
+        stopA = stopB = False
+        is_tncg = params.method == _lib.METHODS["tncg"]
+        is_pg = params.method == _lib.METHODS["pg"]
+        for _ in range(params.numiter):
+            cdiv = float(real(1. / (1. + 2. * float(l2) * float(step))))
+            if not (is_tncg and stopB):
+                n = self.be.half_sweep(_lib.SIDE_CSC, params, float(step), cdiv)
+                self.be.exchange(_lib.SIDE_CSC)
+                if is_tncg and params.early_stop:
+                    stopB = (self.allreduce_int(n) / self.dimB) >= .95
+            if is_pg:
+                step = real(float(step) * 0.5)
+            if not (is_tncg and stopA):
+                n = self.be.half_sweep(_lib.SIDE_CSR, params, float(step), cdiv)
+                self.be.exchange(_lib.SIDE_CSR)
+                if is_tncg and params.early_stop:
+                    stopA = (self.allreduce_int(n) / self.dimA) >= .95
+            if stopA and stopB:
+                break
+
+
+class GpuBackend:
+    """One rank's shard on one GPU: a DeviceFit bound to torch-owned replicas of A and B."""
+
+    def __init__(self, csr, csc, A0, B0, rank, world, device_index, group=None):
+        import torch
+        import torch.distributed as dist
+        from .device import DeviceFit
+        from . import _lib
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = rank, world
+        dimA, k = A0.shape
+        dimB = B0.shape[0]
+        self.dev = torch.device("cuda", device_index)
+        self.fit = DeviceFit(dimA, dimB, k, A0.dtype, device=device_index)
+        ldf = self.fit.ldf
+        tdt = torch.float32 if A0.dtype == np.float32 else torch.float64
+        self.A = torch.zeros((dimA, ldf), dtype=tdt, device=self.dev)
+        self.B = torch.zeros((dimB, ldf), dtype=tdt, device=self.dev)
+        self.A[:, :k].copy_(torch.from_numpy(A0))
+        self.B[:, :k].copy_(torch.from_numpy(B0))
+        self.fit.bind_factors(self.A.data_ptr(), self.B.data_ptr())
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.fit.set_stream(self.stream.cuda_stream)
+        self.rangesA = nnz_balanced_ranges(csr[1], world)
+        self.rangesB = nnz_balanced_ranges(csc[1], world)
+        a0, a1 = self.rangesA[rank]
+        b0, b1 = self.rangesB[rank]
+        lr = slice_compressed(csr, a0, a1)
+        lc = slice_compressed(csc, b0, b1)
+        self.local_nnz = int(lr[0].shape[0])
+        self.fit.set_matrix(_lib.SIDE_CSR, *lr, row_begin=a0, n_rows=a1 - a0)
+        self.fit.set_matrix(_lib.SIDE_CSC, *lc, row_begin=b0, n_rows=b1 - b0)
+        torch.cuda.synchronize(self.dev)
+
+    def half_sweep(self, side, params, step, cdiv):
+        return self.fit.half_sweep(side, params, step, cdiv)
+
+    def exchange(self, side):
+        """Refresh every replica with the owners' fresh rows: one broadcast per owner,
+        in place on the replicated matrix (slices are contiguous row ranges)."""
+        if self.world == 1:
+            return
+        from . import _lib
+        M, ranges = (self.A, self.rangesA) if side == _lib.SIDE_CSR else (self.B, self.rangesB)
+        works = []
+        for r, (lo, hi) in enumerate(ranges):
+            if hi > lo:
+                works.append(self.dist.broadcast(M[lo:hi], src=r, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+
+    def factors(self):
+        k = self.fit.k
+        return self.A[:, :k].cpu().numpy(), self.B[:, :k].cpu().numpy()

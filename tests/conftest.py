@@ -1,0 +1,90 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure the product library and the CPU checkers exist (no-op when prebuilt)."""
+    from poismf_b200 import _lib
+    from oracle import oracle
+    if not os.path.exists(_lib.LIB_PATH):
+        from poismf_b200.build import build
+        build()
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libpoismf_oracle_double.so")):
+        oracle.build()
+    yield
+
+
+def has_gpu():
+    try:
+        from poismf_b200 import _lib
+        return _lib.lib().pmf_b200_device_count() > 0
+    except Exception:
+        return False
+
+
+# ---- shared problem builders -------------------------------------------------
+CASES = {
+    # name: (method, hyper-parameters)   [maxupd None -> 15*k as poismf/__init__.py:252]
+    "pg": ("pg", dict(l2_reg=1e9, step_size=1e-7, maxupd=1, numiter=2)),
+    "pg_w": ("pg", dict(l2_reg=1e3, step_size=1e-4, maxupd=3, numiter=2, w_mult=2.5, l1_reg=0.1)),
+    "cg": ("cg", dict(l2_reg=1e4, maxupd=5, numiter=1, limit_step=True)),
+    "cg_nolimit_w": ("cg", dict(l2_reg=1e3, maxupd=5, numiter=2, limit_step=False, w_mult=1.5)),
+    "tncg": ("tncg", dict(l2_reg=1e3, maxupd=None, numiter=1)),
+    "tncg_reuse_stop": ("tncg", dict(l2_reg=1e2, maxupd=None, numiter=3, reuse_prev=True, early_stop=True, l1_reg=0.5)),
+    "tncg_w": ("tncg", dict(l2_reg=1e3, maxupd=None, numiter=2, w_mult=3.0)),
+}
+
+
+def problem(name, dtype):
+    from poismf_b200.synth import init_factors, powerlaw_counts, readme_counts
+    if name == "readme":
+        csr, csc = readme_counts(dtype=dtype)
+        k = 5
+    elif name == "pl2k":
+        csr, csc = powerlaw_counts(2000, 800, 60000, dtype=dtype)
+        k = 16
+    elif name == "pl6k":
+        csr, csc = powerlaw_counts(6000, 2500, 300000, dtype=dtype)
+        k = 50
+    elif name == "ragged":   # empty rows/cols, single-nnz rows, k not a multiple of 4
+        csr, csc = powerlaw_counts(300, 4000, 2500, alpha_a=1.2, alpha_b=0.3, dtype=dtype, seed=7)
+        k = 7
+    else:
+        raise KeyError(name)
+    dimA, dimB = csr[1].shape[0] - 1, csc[1].shape[0] - 1
+    A0, B0 = init_factors(dimA, dimB, k, dtype=dtype)
+    return csr, csc, A0, B0, k
+
+
+def hyper(case, k):
+    method, kw = CASES[case]
+    kw = dict(kw)
+    if kw["maxupd"] is None:
+        kw["maxupd"] = 15 * k
+    return method, kw
+
+
+def run_device(csr, csc, A, B, method, kw, flags=0):
+    from poismf_b200 import c_funs
+    return c_funs._run_poismf(csr[0], csr[2], csr[1], csc[0], csc[2], csc[1], A, B, method=method,
+                              limit_step=kw.get("limit_step", False), l2_reg=kw["l2_reg"],
+                              l1_reg=kw.get("l1_reg", 0.), w_mult=kw.get("w_mult", 1.),
+                              step_size=kw.get("step_size", 1e-7), niter=kw["numiter"], maxupd=kw["maxupd"],
+                              early_stop=kw.get("early_stop", False), reuse_prev=kw.get("reuse_prev", False),
+                              flags=flags)
+
+
+def row_rel_err(X, Y):
+    return np.linalg.norm(X - Y, axis=1) / np.maximum(np.linalg.norm(Y, axis=1), 1e-30)

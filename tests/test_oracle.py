@@ -1,0 +1,75 @@
+"""CPU tests of the checkers: the plain-C restatement against (a) the reference itself
+(oracle/_ref, when it has been built here) and (b) the committed golden outputs of the
+reference (always).  Bit-exact: both are compiled -O2 -ffp-contract=off with sequential BLAS."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASES, hyper, problem
+from oracle.oracle import Ref, Restatement
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+DTYPES = [np.float64, np.float32]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("prob", ["readme", "ragged"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_restatement_matches_golden(dtype, prob, case):
+    csr, csc, A0, B0, k = problem(prob, dtype)
+    name = np.dtype(dtype).name
+    chk = GOLD[f"{prob}/{name}/csr_checksum"]
+    assert chk[2] == csr[0].shape[0] and chk[0] == csr[0].astype(np.float64).sum(), "synthetic inputs drifted"
+    method, kw = hyper(case, k)
+    A, B = A0.copy(), B0.copy()
+    assert Restatement(dtype).run_poismf(A, B, csr, csc, method, **kw) == 0
+    assert np.array_equal(A, GOLD[f"{prob}/{name}/{case}/A"])
+    assert np.array_equal(B, GOLD[f"{prob}/{name}/{case}/B"])
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", list(CASES))
+def test_restatement_matches_reference_build(dtype, case):
+    csr, csc, A0, B0, k = problem("pl2k", dtype)
+    method, kw = hyper(case, k)
+    A1, B1, A2, B2 = A0.copy(), B0.copy(), A0.copy(), B0.copy()
+    assert Ref(dtype).run_poismf(A1, B1, csr, csc, method, **kw) == 0
+    assert Restatement(dtype).run_poismf(A2, B2, csr, csc, method, **kw) == 0
+    assert np.array_equal(A1, A2) and np.array_equal(B1, B2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_predict_and_topn_match_golden(dtype):
+    name = np.dtype(dtype).name
+    csr, csc, A0, B0, k = problem("readme", dtype)
+    rng = np.random.default_rng(3)
+    ixA = rng.integers(0, A0.shape[0], 257).astype(np.uint64)
+    ixB = rng.integers(0, B0.shape[0], 257).astype(np.uint64)
+    orc = Restatement(dtype)
+    assert np.array_equal(orc.predict_multiple(A0, B0, ixA, ixB), GOLD[f"predict/{name}"])
+    Brand = np.ascontiguousarray(rng.gamma(1, 1, size=B0.shape).astype(dtype))
+    rc, ix, sc = orc.topN(np.ascontiguousarray(A0[3]), Brand, 10)
+    assert rc == 0 and np.array_equal(sc, GOLD[f"topn/{name}/score"]) and np.array_equal(ix, GOLD[f"topn/{name}/ix"])
+    excl = np.arange(0, 1000, 7, dtype=np.uint64)
+    rc, ix, sc = orc.topN(np.ascontiguousarray(A0[3]), Brand, 10, exclude=excl)
+    assert rc == 0 and np.array_equal(sc, GOLD[f"topn_excl/{name}/score"])
+    assert np.array_equal(ix, GOLD[f"topn_excl/{name}/ix"]) and not np.isin(ix, excl).any()
+
+
+def test_topn_argument_checks():
+    orc = Restatement(np.float64)
+    B = np.ones((10, 3)); a = np.ones(3)
+    assert orc.topN(a, B, 0)[0] == 2                                    # n_top == 0
+    assert orc.topN(a, B, 3, include=[1, 2, 3], exclude=[4])[0] == 2    # both lists
+    assert orc.topN(a, B, 5, exclude=list(range(6)))[0] == 2            # n_exclude > n - n_top
+
+
+def test_llk_matches_numpy():
+    csr, csc, A0, B0, k = problem("readme", np.float64)
+    orc = Restatement(np.float64)
+    rows = np.repeat(np.arange(A0.shape[0]), np.diff(csr[1].astype(np.int64)))
+    pred = np.einsum("ij,ij->i", A0[rows], B0[csr[2].astype(np.int64)])
+    want = (csr[0] * np.log(pred)).sum() - A0.sum(0) @ B0.sum(0)
+    assert abs(orc.llk(A0, B0, csr) - want) <= 1e-9 * abs(want)
