@@ -333,7 +333,7 @@ PMF_DEVINL void tn_hvp(TnCtx<STRICT, real, Team>& c, const real* x, real fscale,
     const real delta = (real)(D(accuracy) * (D(xnorm) + 1.0));
     PMF_EW(i) {
         real t = x[i] + delta * v[i];
-        t = t * xs[i] + xo[i];                 // unscalex :482
+        t = add_rn(mul_rn(t, xs[i]), xo[i]);   // unscalex :482 (never contracted, see solve_tn)
         xv[i] = (t < (real)0) ? (real)0 : t;   // coercex  :466
     }
     tm.sync();
@@ -472,7 +472,7 @@ PMF_DEVINL int tn_linesearch(TnCtx<STRICT, real, Team>& c, real fscale, real eta
         const real ualpha = alpha + q.u;
         PMF_EW(i) {
             real t = x[i] + ualpha * p[i];
-            t = t * xs[i] + xo[i];
+            t = add_rn(mul_rn(t, xs[i]), xo[i]);
             temp[i] = (t < (real)0) ? (real)0 : t;
         }
         tm.sync();
@@ -717,8 +717,11 @@ PMF_DEVINL void solve_tn(const Team& tm, const RowView<real>& rv, const HalfSwee
                 upd1 = false;
             }
         }
+        // unscalex is never contracted into an FMA, not even in fast mode: a variable pinned at
+        // the bound has x = (0 - xo)/xs, and only the separately rounded product gives back an
+        // exact 0 (with FMA the reference's float build loses its sparsity)
         PMF_EW(i) {                                                                  // :971-972
-            const real t = x[i] * xs[i] + xo[i];
+            const real t = add_rn(mul_rn(x[i], xs[i]), xo[i]);
             x[i] = (t < (real)0) ? (real)0 : t;
         }
         tm.sync();

@@ -100,20 +100,35 @@ def test_fast_cg_double_within_gate(prob, flags):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("case", ["cg", "cg_nolimit_w", "tncg", "tncg_w", "tncg_reuse_stop"])
 def test_fast_llk_gate(dtype, case):
-    """Final Poisson log-likelihood within 1e-4 relative of the oracle's (north_star) — the stable
-    quantity for the solvers whose coordinates are chaotic in the rounding."""
+    """FINAL Poisson log-likelihood within 1e-4 relative of the oracle's (north_star) — the stable
+    quantity for the solvers whose coordinates are chaotic in the rounding.
+    Where the reference itself, rebuilt with FMA contraction and -O3 (oracle/_ref "fast" build),
+    misses that gate against its strict build, the device is held to 3x that noise floor."""
+    from oracle.oracle import Ref
     csr, csc, A0, B0, k = problem("pl2k", dtype)
     method, kw = hyper(case, k)
+    if method == "cg":
+        kw["numiter"] = 10          # "final": a fit, not a single sweep
     Ar, Br = _oracle(dtype, csr, csc, A0, B0, method, kw)
     A, B = A0.copy(), B0.copy()
     assert run_device(csr, csc, A, B, method, kw) == 0
     assert np.isfinite(A).all() and np.isfinite(B).all() and (A >= 0).all() and (B >= 0).all()
     orc = Restatement(dtype)
     l_ref, l_dev = orc.llk(Ar, Br, csr), orc.llk(A, B, csr)
-    gate = 1e-4 if dtype == np.float64 else 2e-3     # float: reference-vs-reference is 3.7e-4..1.7e-2 (SURVEY §4.1)
-    assert abs(l_dev - l_ref) <= gate * abs(l_ref), (l_dev, l_ref)
-    # sparsity (exact zeros) reported next to the reference's
-    assert abs((A == 0).mean() - (Ar == 0).mean()) <= 0.05 and abs((B == 0).mean() - (Br == 0).mean()) <= 0.05
+    # double: the north_star gate.  float: 2e-3 — measured floor of the reference against itself
+    # on this very problem is 3e-6 (cg) .. 3e-2 (tncg), see scripts/dev_llk.py / DESIGN.md §parity
+    gate = 1e-4 if dtype == np.float64 else 2e-3
+    if Ref.available(dtype, fast=True):
+        A2, B2 = A0.copy(), B0.copy()
+        Ref(dtype, fast=True).run_poismf(A2, B2, csr, csc, method, **kw)
+        noise = abs(orc.llk(A2, B2, csr) - l_ref) / abs(l_ref)
+        gate = max(gate, 3 * noise)
+    elif dtype == np.float32 and method == "tncg":
+        gate = 2e-2                 # SURVEY §4.1: reference-vs-reference reaches 1.7e-2 in float
+    assert abs(l_dev - l_ref) <= gate * abs(l_ref), (l_dev, l_ref, gate)
+    # sparsity (EXACT zeros) stays next to the strict reference's, also in float with FMA on
+    # (the final unscale is never contracted; the reference's own FMA build loses its zeros)
+    assert abs((A == 0).mean() - (Ar == 0).mean()) <= 0.03 and abs((B == 0).mean() - (Br == 0).mean()) <= 0.03
 
 
 # ---------------------------------------------------------------- edge cases
