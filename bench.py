@@ -57,6 +57,10 @@ def make_problem(cfg, dtype=np.float32):
     return csr, csc, A0, B0
 
 
+def team_name(code):
+    return f"lanes{-code}" if code < 0 else ("block" if code == 1 else f"cluster{code}")
+
+
 def algorithmic_bytes(nnz, rows, other, k, s):
     """bytes of one half-sweep = nnz*(k*s + s + 4) + rows*(2*k*s + 8) + other*k*s."""
     return nnz * (k * s + s + 4) + rows * (2 * k * s + 8) + other * k * s
@@ -262,12 +266,12 @@ def main():
         sweep_bytes = algorithmic_bytes(nnz, dimA, dimB, k, s) + algorithmic_bytes(nnz, dimB, dimA, k, s)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": which,
-                "kernel": f"rows_{'block' if top['block_team'] else 'warp'}_kernel<{cfg['method']}> side="
+                "kernel": f"rows_{team_name(top['block_team'])}_kernel<{cfg['method']}> side="
                           f"{'CSR(A)' if top['side'] == 0 else 'CSC(B)'} cap={top['cap']} rows={top['nrows']} nnz={top['nnz']}",
                 "kernel_avg_ms": avg_ms, "kernel_share_of_step": top["ms"] / max(ms_total, 1e-9),
                 "sweep_algorithmic_GBps": sweep_bytes / (ms_step / 1e3) / 1e9,
                 "sweep_frac_of_peak": sweep_bytes / (ms_step / 1e3) / 1e9 / peak,
-                "bins": [{"side": p["side"], "team": "block" if p["block_team"] else "warp", "cap": p["cap"],
+                "bins": [{"side": p["side"], "team": team_name(p["block_team"]), "cap": p["cap"],
                           "rows": p["nrows"], "nnz": p["nnz"], "ms_per_sweep": p["ms"] / args.steps} for p in prof]}
 
     # e2e: drop-in run_poismf with host buffers (rank 0 alone at N=1; sharded path otherwise reuses value)

@@ -91,7 +91,7 @@ int pmf_b200_sync(pmf_b200_handle* h);
  * for bench.py's roofline line: one entry per (side, row bin). */
 typedef struct pmf_b200_bin_profile {
     int side;                  /* PMF_SIDE_CSR / PMF_SIDE_CSC */
-    int block_team;            /* 0: warp per row, 1: CTA per row */
+    int block_team;            /* < 0: -lanes per row (sub-warp / warp teams); 1: CTA per row; > 1: CTAs per row (cluster) */
     int cap;                   /* staged tile capacity (0: tile read from global memory) */
     int nrows;                 /* rows in the bin */
     unsigned long long nnz;    /* non-zeros in the bin */

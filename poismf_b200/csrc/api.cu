@@ -77,6 +77,8 @@ static int tile_stride(int k, int V)
 // ---------------------------------------------------------------------------
 struct Bin {
     bool block = false;     // CTA per row (else warp per row)
+    int cluster = 1;        // > 1: a thread-block cluster of this many CTAs per row
+    int width = 32;         // lanes per row for the warp-level bins
     int cap = 0;            // staged tile capacity; 0 = tile stays in global memory
     int threads = 256;
     size_t slice = 0, smem = 0;
@@ -277,23 +279,26 @@ template <class real> struct HandleT : pmf_b200_handle {
                    (size_t)4 * cap * sizeof(real) + (size_t)cap * kp * sizeof(real);
         return round_up_sz(b, 16);
     }
-    int plan(Side<real>& S, int method)
+    int plan(Side<real>& S, int method, bool strict)
     {
-        if (S.planned_method == method) return 0;
+        const int key = method * 2 + (strict ? 1 : 0);
+        if (S.planned_method == key) return 0;
         S.free_plan();
         const int nvec = method == PMF_PG ? 3 : (method == PMF_CG ? 7 : TN_NUM_VECS);
         std::vector<Bin> bins;
-        // warp-per-row bins
-        const int wcaps[3] = {32, 64, 128};
-        for (int c = 0; c < 3; c++) {
+        // (sub-)warp-per-row bins: {lanes per row, tile capacity}; sub-warps in fast numerics only
+        const int wdef[4][2] = {{8, 16}, {16, 32}, {32, 64}, {32, 128}};
+        for (int c = 0; c < 4; c++) {
+            const int width = wdef[c][0];
+            if (strict && width < 32) continue;
             Bin b;
-            b.block = false; b.cap = wcaps[c];
-            b.slice = slice_bytes(32, nvec, b.cap);
-            int warps = 8;
-            while (warps > 1 && b.slice * warps > SMEM_CTA_MAX) warps >>= 1;
-            if (b.slice * warps > SMEM_CTA_MAX) continue;
-            b.threads = warps * 32;
-            b.smem = b.slice * warps;
+            b.block = false; b.cap = wdef[c][1]; b.width = width;
+            b.slice = slice_bytes(width, nvec, b.cap);
+            int teams = 256 / width;
+            while (teams > 1 && b.slice * teams > SMEM_CTA_MAX) teams >>= 1;
+            if (b.slice * teams > SMEM_CTA_MAX) continue;
+            b.threads = std::max(teams * width, 32);
+            b.smem = b.slice * (b.threads / width);
             bins.push_back(b);
         }
         // CTA-per-row bins: largest capacity with 4, 2, 1 resident CTAs per SM
@@ -313,7 +318,25 @@ template <class real> struct HandleT : pmf_b200_handle {
             bins.push_back(b);
             last_cap = cap;
         }
-        {   // everything longer: tile stays in global memory / L2
+        if (!strict) {
+            // cluster-per-row bins: G CTAs stage G slices of the tile (fast numerics only)
+            const size_t fixed = slice_bytes(256, nvec, 0) + GANG_XBYTES + 16;
+            int gcap = (int)((SMEM_CTA_MAX - fixed) / ((size_t)(kp + 4) * sizeof(real)));
+            gcap = gcap / 4 * 4;
+            const int gs[4] = {2, 4, 8, 16};
+            for (int c = 0; c < 4 && gcap > 0; c++) {
+                Bin b;
+                b.block = true; b.cluster = gs[c]; b.cap = gcap; b.threads = 256;
+                b.slice = slice_bytes(256, nvec, gcap) + GANG_XBYTES;
+                b.smem = b.slice;
+                bins.push_back(b);
+            }
+            Bin b;     // beyond 16 resident slices: 16 CTAs, each streaming its slice from L2
+            b.block = true; b.cluster = 16; b.cap = 0; b.threads = 256;
+            b.slice = slice_bytes(256, nvec, 0) + GANG_XBYTES;
+            b.smem = b.slice;
+            bins.push_back(b);
+        } else {   // strict numerics: everything longer stays on one CTA, tile in global memory / L2
             Bin b;
             b.block = true; b.cap = 0; b.threads = 256;
             b.slice = slice_bytes(256, nvec, 0);
@@ -325,7 +348,7 @@ template <class real> struct HandleT : pmf_b200_handle {
             const long long n = S.h_ptr[r + 1] - S.h_ptr[r];
             if (n == 0) { empty.push_back((int)r); continue; }
             size_t bi = 0;
-            while (bi + 1 < bins.size() && n > bins[bi].cap) bi++;
+            while (bi + 1 < bins.size() && n > (long long)bins[bi].cap * bins[bi].cluster) bi++;
             bins[bi].rows.push_back((int)r);
             bins[bi].max_nnz = std::max(bins[bi].max_nnz, n);
             bins[bi].nnz += (unsigned long long)n;
@@ -351,13 +374,16 @@ template <class real> struct HandleT : pmf_b200_handle {
             CK(cudaMemcpyAsync(S.d_empty, empty.data(), empty.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
         const Bin& gb = bins.back();
         if (!gb.rows.empty()) {
-            S.gs_stride = (long long)round_up_sz((size_t)gb.max_nnz, 4);
-            S.gs_ctas = (int)std::min<size_t>(gb.rows.size(), (size_t)num_sms);
+            // per-CTA scratch for the three per-non-zero arrays of rows that are not staged
+            const long long per_cta = (gb.max_nnz + gb.cluster - 1) / gb.cluster;
+            S.gs_stride = (long long)round_up_sz((size_t)per_cta + 4, 4);
+            S.gs_ctas = gb.cluster > 1 ? num_sms
+                                       : (int)std::min<size_t>(gb.rows.size(), (size_t)num_sms);
             CK(cudaMalloc(&S.gscratch, (size_t)S.gs_ctas * 3 * S.gs_stride * sizeof(real)));
         }
         CK(cudaStreamSynchronize(stream));
         S.bins.swap(bins);
-        S.planned_method = method;
+        S.planned_method = key;
         return 0;
     }
 
@@ -392,8 +418,8 @@ template <class real> struct HandleT : pmf_b200_handle {
         Side<real>& S = sides[side];
         if (!S.ptr) return fail("half_sweep: matrix for side %d not set", side);
         if (p.method != PMF_PG && p.method != PMF_CG && p.method != PMF_TNCG) return fail("bad method");
-        if (plan(S, p.method)) return 1;
         const bool strict = (p.flags & PMF_FLAG_STRICT) != 0;
+        if (plan(S, p.method, strict)) return 1;
         const bool updA = side == PMF_SIDE_CSR;
         real* M = updA ? A : B;
         const real* F = updA ? B : A;
@@ -446,17 +472,21 @@ template <class real> struct HandleT : pmf_b200_handle {
             cfg.threads = b.threads;
             cfg.smem_bytes = b.smem;
             cfg.stream = stream;
-            const int warps = b.threads / 32;
-            cfg.needed = b.block ? P.nrows : (P.nrows + warps - 1) / warps;
-            cfg.max_grid = b.cap == 0 ? S.gs_ctas : (1 << 30);
+            const int teams = b.threads / b.width;
+            cfg.needed = b.block ? P.nrows : (P.nrows + teams - 1) / teams;
+            cfg.team_width = b.width;
+            cfg.max_grid = b.cap == 0 ? S.gs_ctas / b.cluster : (1 << 30);
             cfg.num_sms = num_sms;
+            cfg.cluster = b.cluster;
             cudaError_t e;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) {
                 CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
                 CK(cudaEventRecord(ev0, stream));
             }
-            if (p.method == PMF_TNCG)
+            if (b.cluster > 1)
+                e = p.method == PMF_TNCG ? launch_gang_tn_fast<real>(cfg, P) : launch_gang_pgcg_fast<real>(cfg, P);
+            else if (p.method == PMF_TNCG)
                 e = strict ? launch_rows_tn_strict<real>(cfg, P) : launch_rows_tn_fast<real>(cfg, P);
             else
                 e = strict ? launch_rows_pgcg_strict<real>(cfg, P) : launch_rows_pgcg_fast<real>(cfg, P);
@@ -491,7 +521,7 @@ template <class real> struct HandleT : pmf_b200_handle {
             for (auto& b : sides[sd].bins) {
                 if (b.rows.empty() || n >= max_entries) continue;
                 pmf_b200_bin_profile& o = out[n++];
-                o.side = sd; o.block_team = b.block; o.cap = b.cap; o.nrows = (int)b.rows.size();
+                o.side = sd; o.block_team = b.block ? b.cluster : -b.width; o.cap = b.cap; o.nrows = (int)b.rows.size();
                 o.nnz = b.nnz; o.launches = b.ev.size() / 2; o.ms = 0;
                 for (size_t i = 0; i + 1 < b.ev.size(); i += 2) {
                     float ms = 0;

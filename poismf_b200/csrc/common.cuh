@@ -93,59 +93,126 @@ PMF_DEVINL bool is_bad(double v) { return isnan(v) || isinf(v); }
 // ---------------------------------------------------------------------------
 // Teams
 // ---------------------------------------------------------------------------
-// A team exposes: rank(), size(), sync(), bcast-capable reductions.  All
-// reductions return the SAME bits to every member (solver control flow is
-// executed redundantly by all members and must not diverge).
-struct WarpTeam {
-    int lane;
-    PMF_DEVINL explicit WarpTeam(void* /*scratch*/) : lane(threadIdx.x & 31) {}
-    PMF_DEVINL int rank() const { return lane; }
-    PMF_DEVINL int size() const { return 32; }
-    PMF_DEVINL void sync() const { __syncwarp(); }
-    template <class T> PMF_DEVINL T sum(T v) const
-    {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    }
-    template <class T> PMF_DEVINL T min(T v) const
-    {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { T w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
-        return v;
-    }
-    template <class T> PMF_DEVINL T max(T v) const
-    {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { T w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
-        return v;
-    }
-    template <class T> PMF_DEVINL T bcast0(T v) const { return __shfl_sync(0xffffffffu, v, 0); }
-};
+// A team is the group of threads that cooperates on one row.  It exposes
+//   rank()/size()/sync()      : split of the per-non-zero loops and of the "owner" k-loops
+//   sum/min/max/bcast0        : team-wide reductions (block-level ones cost two barriers)
+//   kbegin()/kstride()/ksum() : REDUNDANT k-vector reductions — every warp (or sub-warp) of
+//                               the team walks the whole k-vector itself and reduces with
+//                               shuffles, so a dot product of two shared k-vectors needs no
+//                               barrier at all (k <= 256: at most 8 elements per lane)
+//   nnz_sum*/nnz_vec_sum      : sums over the row's non-zeros (span the cluster for gangs)
+// All reductions return the SAME bits to every member: the solver's control flow is
+// executed redundantly by all members and must not diverge.
+template <class T> PMF_DEVINL T warp_sum(T v, unsigned mask = 0xffffffffu, int width = 32)
+{
+    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <class T> PMF_DEVINL T warp_min(T v, unsigned mask = 0xffffffffu, int width = 32)
+{
+    for (int o = width >> 1; o > 0; o >>= 1) { T w = __shfl_xor_sync(mask, v, o); v = w < v ? w : v; }
+    return v;
+}
+template <class T> PMF_DEVINL T warp_max(T v, unsigned mask = 0xffffffffu, int width = 32)
+{
+    for (int o = width >> 1; o > 0; o >>= 1) { T w = __shfl_xor_sync(mask, v, o); v = w > v ? w : v; }
+    return v;
+}
 
-// One CTA per row.  `scratch` points at >= 34 doubles of shared memory.
-struct BlockTeam {
+// W lanes of a warp (W = 8, 16 or 32) per row: 32/W short rows advance side by side in one
+// warp.  All synchronisation uses the sub-warp's own lane mask, so sub-warps of one warp may
+// follow different control flow.
+template <int W> struct SubWarpTeam {
+    int lane;        // rank within the team
+    unsigned mask;   // lanes of this team within the warp
+    PMF_DEVINL explicit SubWarpTeam(void* /*scratch*/)
+    {
+        const int wl = threadIdx.x & 31;
+        lane = wl & (W - 1);
+        mask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << (wl & ~(W - 1)));
+    }
+    PMF_DEVINL int rank() const { return lane; }
+    PMF_DEVINL int size() const { return W; }
+    PMF_DEVINL void sync() const { __syncwarp(mask); }
+    template <class T> PMF_DEVINL T sum(T v) const { return warp_sum(v, mask, W); }
+    template <class T> PMF_DEVINL T min(T v) const { return warp_min(v, mask, W); }
+    template <class T> PMF_DEVINL T max(T v) const { return warp_max(v, mask, W); }
+    template <class T> PMF_DEVINL T bcast0(T v) const { return __shfl_sync(mask, v, 0, W); }
+    PMF_DEVINL int kbegin() const { return lane; }
+    PMF_DEVINL int kstride() const { return W; }
+    template <class T> PMF_DEVINL T ksum(T v) const { return warp_sum(v, mask, W); }
+    template <class T> PMF_DEVINL T kmin(T v) const { return warp_min(v, mask, W); }
+    template <class T> PMF_DEVINL T kmax(T v) const { return warp_max(v, mask, W); }
+    static constexpr bool is_gang = false;
+    PMF_DEVINL bool owns_row() const { return true; }
+    PMF_DEVINL unsigned crank_() const { return 0; }
+    PMF_DEVINL unsigned csize_() const { return 1; }
+    template <class T> PMF_DEVINL T nnz_sum(T v) const { return sum(v); }
+    template <class T, int N> PMF_DEVINL void nnz_sum_n(T (&v)[N]) const
+    {
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = sum(v[j]);
+    }
+    template <class real> PMF_DEVINL void nnz_vec_sum(real*, int) const {}
+};
+using WarpTeam = SubWarpTeam<32>;
+
+// CTA-level reductions shared by BlockTeam and ClusterTeam.  `red` = 34 doubles of shared
+// memory.  Second stage by shuffles: no serial fold, same bits on every thread.
+struct BlockOps {
     double* red;
-    PMF_DEVINL explicit BlockTeam(void* scratch) : red((double*)scratch) {}
     PMF_DEVINL int rank() const { return threadIdx.x; }
     PMF_DEVINL int size() const { return blockDim.x; }
     PMF_DEVINL void sync() const { __syncthreads(); }
-    template <class T, class OP> PMF_DEVINL T reduce(T v, OP op) const
+    PMF_DEVINL int kbegin() const { return threadIdx.x & 31; }
+    PMF_DEVINL int kstride() const { return 32; }
+    template <class T> PMF_DEVINL T ksum(T v) const { return warp_sum(v); }
+    template <class T> PMF_DEVINL T kmin(T v) const { return warp_min(v); }
+    template <class T> PMF_DEVINL T kmax(T v) const { return warp_max(v); }
+    // up to 4 sums at once with one pair of barriers (blockDim <= 256)
+    template <class T, int N> PMF_DEVINL void sum_n(T (&v)[N]) const
+    {
+        static_assert(N <= 4, "at most 4 values per block reduction");
+        T* r = (T*)red;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = warp_sum(v[j]);
+        __syncthreads();   // protect `red` against the previous reduction's readers
+        if (lane == 0)
+#pragma unroll
+            for (int j = 0; j < N; j++) r[j * 8 + w] = v[j];
+        __syncthreads();
+        // lane l = j*8 + w holds one partial; fold the 8-lane groups with shuffles
+        T part = ((lane & 7) < nw && (lane >> 3) < N) ? r[lane] : (T)0;
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = __shfl_sync(0xffffffffu, part, j * 8);
+    }
+    template <class T> PMF_DEVINL T sum(T v) const
+    {
+        T a[1] = {v};
+        sum_n(a);
+        return a[0];
+    }
+    template <class T, class OP> PMF_DEVINL T reduce_idem(T v, OP op) const   // idempotent ops only
     {
         T* r = (T*)red;
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
-        __syncthreads();  // protect `red` against the previous reduction's readers
+        __syncthreads();
         if (lane == 0) r[w] = v;
         __syncthreads();
-        T acc = r[0];
-        for (int i = 1; i < nw; i++) acc = op(acc, r[i]);  // same order on every thread
-        return acc;
+        T part = r[(lane & 7) < nw ? (lane & 7) : 0];
+        part = op(part, __shfl_xor_sync(0xffffffffu, part, 4));
+        part = op(part, __shfl_xor_sync(0xffffffffu, part, 2));
+        part = op(part, __shfl_xor_sync(0xffffffffu, part, 1));
+        return part;
     }
-    template <class T> PMF_DEVINL T sum(T v) const { return reduce(v, [](T a, T b) { return a + b; }); }
-    template <class T> PMF_DEVINL T min(T v) const { return reduce(v, [](T a, T b) { return b < a ? b : a; }); }
-    template <class T> PMF_DEVINL T max(T v) const { return reduce(v, [](T a, T b) { return b > a ? b : a; }); }
+    template <class T> PMF_DEVINL T min(T v) const { return reduce_idem(v, [](T a, T b) { return b < a ? b : a; }); }
+    template <class T> PMF_DEVINL T max(T v) const { return reduce_idem(v, [](T a, T b) { return b > a ? b : a; }); }
     template <class T> PMF_DEVINL T bcast0(T v) const
     {
         T* r = (T*)red;
@@ -154,6 +221,18 @@ struct BlockTeam {
         __syncthreads();
         return r[33];
     }
+};
+
+// One CTA per row.  `scratch` points at >= 34 doubles of shared memory.
+struct BlockTeam : BlockOps {
+    PMF_DEVINL explicit BlockTeam(void* scratch) { red = (double*)scratch; }
+    static constexpr bool is_gang = false;
+    PMF_DEVINL bool owns_row() const { return true; }
+    PMF_DEVINL unsigned crank_() const { return 0; }
+    PMF_DEVINL unsigned csize_() const { return 1; }
+    template <class T> PMF_DEVINL T nnz_sum(T v) const { return sum(v); }
+    template <class T, int N> PMF_DEVINL void nnz_sum_n(T (&v)[N]) const { sum_n(v); }
+    template <class real> PMF_DEVINL void nnz_vec_sum(real*, int) const {}
 };
 
 // ---------------------------------------------------------------------------
@@ -170,8 +249,8 @@ PMF_DEVINL real vdot(const Team& tm, const real* x, const real* y, int k)
         return tm.bcast0(s);
     }
     real s = 0;
-    for (int i = tm.rank(); i < k; i += tm.size()) s = fma(x[i], y[i], s);
-    return tm.sum(s);
+    for (int i = tm.kbegin(); i < k; i += tm.kstride()) s = fma(x[i], y[i], s);
+    return tm.ksum(s);
 }
 // sqrt(sum x^2) — the shim's nrm2 (oracle/blas_shim.c)
 template <bool STRICT, class real, class Team>

@@ -6,6 +6,7 @@
 // of a persistent grid whose teams fetch rows from a list sorted by decreasing
 // length (longest-processing-time-first) through an atomic counter.
 #pragma once
+#include "cluster_team.cuh"
 #include "solver_pg_cg.cuh"
 #include "solver_tn.cuh"
 
@@ -36,16 +37,20 @@ PMF_DEVINL int num_vecs(int method)
 }
 
 // Shared-memory slice of one team:
-//   [team scratch 288 B][gscr team*16 B][vectors NV*kp][xv,pa,pb,pc: 4*cap][tile cap*kp]
+//   [team scratch 288 B][cluster exchange 2*272*8 B (gangs only)][gscr team*16 B][vectors NV*kp]
+//   [xv,pa,pb,pc: 4*cap][tile cap*kp]
+constexpr int GANG_XBYTES = 2 * GANG_XSLOTS * 8;
 template <class real> struct Slice {
     void* team_scratch;
+    void* xchg;
     real* gscr;
     real* vecs;
     real *xv, *pa, *pb, *pc;
     real* tile;
-    PMF_DEVINL Slice(unsigned char* base, int team_size, int nvec, int kp, int cap)
+    PMF_DEVINL Slice(unsigned char* base, int team_size, int nvec, int kp, int cap, bool gang = false)
     {
         team_scratch = base; base += 288;
+        xchg = base; if (gang) base += GANG_XBYTES;
         gscr = (real*)base; base += (size_t)team_size * 16;
         vecs = (real*)base; base += (size_t)nvec * kp * sizeof(real);
         xv = (real*)base; pa = xv + cap; pb = pa + cap; pc = pb + cap;
@@ -58,8 +63,16 @@ template <class real, int METHOD, bool STRICT, bool CACHED, class Team>
 PMF_DEVINL void process_row(const Team& tm, const SideParams<real>& P, const Slice<real>& S,
                             int row, real* gscratch_cta)
 {
-    const long long beg = P.ptr[row];
-    const int n = (int)(P.ptr[row + 1] - beg);
+    long long beg = P.ptr[row];
+    int n = (int)(P.ptr[row + 1] - beg);
+    if (Team::is_gang) {
+        // this CTA's contiguous slice of the row's non-zeros
+        const int chunk = (((n + (int)tm.csize_() - 1) / (int)tm.csize_()) + 3) & ~3;
+        const int t0 = min(n, (int)tm.crank_() * chunk);
+        const int t1 = min(n, t0 + chunk);
+        beg += t0;
+        n = t1 - t0;
+    }
     const int k = P.k, kp = P.kp;
     RowView<real> rv;
     rv.F = P.F; rv.ind = P.ind + beg; rv.n = n; rv.k = k; rv.kp = kp; rv.ldf = P.ldf;
@@ -69,7 +82,7 @@ PMF_DEVINL void process_row(const Team& tm, const SideParams<real>& P, const Sli
     for (int i = tm.rank(); i < nvec * kp; i += tm.size()) S.vecs[i] = (real)0;
     if (P.cap > 0 && n <= P.cap) {
         rv.tile = S.tile; rv.xv = S.xv; rv.pa = S.pa; rv.pb = S.pb; rv.pc = S.pc;
-        stage_tile(tm, P.F, rv.ind, P.xv + beg, n, P.ldf, kp, S.tile, S.xv);
+        stage_tile(tm, P.F, rv.ind, P.xv + beg, n, P.ldf, kp, S.tile, S.xv, reinterpret_cast<int*>(S.pa));
     } else {
         rv.tile = nullptr; rv.xv = P.xv + beg;
         rv.pa = gscratch_cta; rv.pb = gscratch_cta + P.gs_stride; rv.pc = gscratch_cta + 2 * P.gs_stride;
@@ -94,27 +107,31 @@ PMF_DEVINL void process_row(const Team& tm, const SideParams<real>& P, const Sli
         CgVecs<real> vv;
         vv.x = x; vv.csum = csum;
         vv.g0 = V + 2 * kp; vv.g1 = V + 3 * kp; vv.d0 = V + 4 * kp; vv.d1 = V + 5 * kp; vv.xnew = V + 6 * kp;
-        if (CACHED && P.hc.limit_step) solve_cg<STRICT, true>(tm, rv, P.hc, vv);
-        else solve_cg<STRICT, false>(tm, rv, P.hc, vv);
+        if (CACHED && !STRICT && P.hc.limit_step) solve_cg_cached(tm, rv, P.hc, vv);
+        else solve_cg<STRICT>(tm, rv, P.hc, vv);
     } else {
         solve_tn<STRICT>(tm, rv, P.hc, V, Mrow, P.n_unchanged);
     }
     tm.sync();
-    for (int i = tm.rank(); i < k; i += tm.size()) Mrow[i] = x[i];
+    if (tm.owns_row())
+        for (int i = tm.rank(); i < k; i += tm.size()) Mrow[i] = x[i];
     tm.sync();
 }
 
-template <class real, int METHOD, bool STRICT, bool CACHED>
+// W lanes per row (W = 32: a warp per row; W = 8, 16: several short rows side by side in one
+// warp).  Each team owns one slice of the CTA's dynamic shared memory and fetches rows from
+// the bin's list through an atomic counter.
+template <class real, int METHOD, bool STRICT, bool CACHED, int W>
 __global__ void __launch_bounds__(256) rows_warp_kernel(const SideParams<real> P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5;
-    Slice<real> S(smem + (size_t)warp * P.slice_bytes, 32, num_vecs(METHOD), P.kp, P.cap);
-    WarpTeam tm(S.team_scratch);
+    const int team_id = threadIdx.x / W;
+    Slice<real> S(smem + (size_t)team_id * P.slice_bytes, W, num_vecs(METHOD), P.kp, P.cap);
+    SubWarpTeam<W> tm(S.team_scratch);
     for (;;) {
         int idx = 0;
         if (tm.lane == 0) idx = atomicAdd(P.counter, 1);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
+        idx = tm.bcast0(idx);
         if (idx >= P.nrows) break;
         process_row<real, METHOD, STRICT, CACHED>(tm, P, S, P.rows[idx], (real*)nullptr);
     }
@@ -136,6 +153,23 @@ __global__ void __launch_bounds__(256) rows_block_kernel(const SideParams<real> 
         if (idx >= P.nrows) break;
         process_row<real, METHOD, STRICT, CACHED>(tm, P, S, P.rows[idx], gs);
     }
+}
+
+// One thread-block cluster per heavy row (fast numerics only: the cross-CTA fold changes
+// the summation order).  Rows are dealt round-robin to the clusters, longest first.
+template <class real, int METHOD, bool CACHED>
+__global__ void __launch_bounds__(256) rows_cluster_kernel(const SideParams<real> P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::cluster_group cl = cg::this_cluster();
+    Slice<real> S(smem, blockDim.x, num_vecs(METHOD), P.kp, P.cap, true);
+    ClusterTeam tm(S.team_scratch, S.xchg);
+    const int csize = (int)cl.num_blocks();
+    const int cluster_id = blockIdx.x / csize, nclusters = gridDim.x / csize;
+    real* gs = P.gscratch ? P.gscratch + (size_t)blockIdx.x * 3 * P.gs_stride : nullptr;
+    for (int idx = cluster_id; idx < P.nrows; idx += nclusters)
+        process_row<real, METHOD, false, CACHED>(tm, P, S, P.rows[idx], gs);
+    cl.sync();   // nobody leaves while a peer may still read its shared memory
 }
 
 }  // namespace pmf

@@ -8,7 +8,8 @@ namespace pmf {
 template <class real> struct SideParams;
 
 struct LaunchCfg {
-    bool block_team;     // false: one warp per row; true: one CTA per row
+    bool block_team;     // false: `team_width` lanes per row; true: one CTA per row
+    int team_width;      // 8, 16 or 32 (sub-warp teams exist in fast numerics only)
     bool cached;         // cg: re-use <x,F_t>, <d,F_t> in the line search (fast mode, limit_step)
     int threads;
     size_t smem_bytes;
@@ -16,11 +17,15 @@ struct LaunchCfg {
     int needed;          // CTAs needed to give every row its own team
     int max_grid;        // upper bound on the grid (global-scratch bin)
     int num_sms;
+    int cluster;         // CTAs per row (thread-block cluster size); <= 1: no cluster
 };
 
 template <class real> cudaError_t launch_rows_pgcg_fast(const LaunchCfg&, const SideParams<real>&);
 template <class real> cudaError_t launch_rows_pgcg_strict(const LaunchCfg&, const SideParams<real>&);
 template <class real> cudaError_t launch_rows_tn_fast(const LaunchCfg&, const SideParams<real>&);
 template <class real> cudaError_t launch_rows_tn_strict(const LaunchCfg&, const SideParams<real>&);
+// cluster-per-row kernels exist in fast numerics only
+template <class real> cudaError_t launch_gang_pgcg_fast(const LaunchCfg&, const SideParams<real>&);
+template <class real> cudaError_t launch_gang_tn_fast(const LaunchCfg&, const SideParams<real>&);
 
 }  // namespace pmf

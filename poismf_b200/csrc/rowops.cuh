@@ -73,20 +73,27 @@ template <class real> struct RowView {
     }
 };
 
-// Gather the row's tile (and its values) into shared memory.
+// Gather the row's tile (and its values) into shared memory.  The indices are first copied
+// to shared memory (coalesced; `idx_s` may alias one of the per-non-zero scratch arrays), so
+// that the 16-byte cp.async gathers are not chained behind global index loads.
 template <class real, class Team>
 PMF_DEVINL void stage_tile(const Team& tm, const real* __restrict__ F, const int* __restrict__ ind,
                            const real* __restrict__ xv_g, int n, int ldf, int kp,
-                           real* tile, real* xv_s)
+                           real* tile, real* xv_s, int* idx_s)
 {
     constexpr int V = RealTraits<real>::V;
     const int L = ldf / V;  // 16-byte chunks per factor row
-    const int total = n * L;
-    for (int idx = tm.rank(); idx < total; idx += tm.size()) {
-        const int t = idx / L, c = idx - t * L;
-        cp_async16(tile + (size_t)t * kp + c * V, F + (size_t)ind[t] * ldf + c * V);
+    for (int t = tm.rank(); t < n; t += tm.size()) { idx_s[t] = ind[t]; xv_s[t] = xv_g[t]; }
+    tm.sync();
+    // thread -> (row t, chunk c), advanced without divisions
+    const int sz = tm.size();
+    const int dq = sz / L, dr = sz - dq * L;
+    int t = tm.rank() / L, c = tm.rank() - t * L;
+    while (t < n) {
+        cp_async16(tile + (size_t)t * kp + c * V, F + (size_t)idx_s[t] * ldf + c * V);
+        t += dq; c += dr;
+        if (c >= L) { c -= L; t++; }
     }
-    for (int t = tm.rank(); t < n; t += tm.size()) xv_s[t] = xv_g[t];
     cp_async_wait_all();
     tm.sync();
 }
@@ -161,6 +168,7 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
     const int sz = tm.size(), rk = tm.rank();
     VT* scr = reinterpret_cast<VT*>(rv.gscr);
     VT* gv = reinterpret_cast<VT*>(g);
+    // partial sums of this team's (slice of the) non-zeros go to `tot` = scr[0..L)
     if (L <= sz) {
         const int groups = sz / L;
         const int grp = rk / L, c = rk - grp * L;
@@ -168,13 +176,26 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
         vzero(acc0); vzero(acc1);
         if (grp < groups) {
             int t = grp;
-            for (; t + groups < n; t += 2 * groups) {
-                const VT b0 = reinterpret_cast<const VT*>(rv.rowp(t))[c];
-                const VT b1 = reinterpret_cast<const VT*>(rv.rowp(t + groups))[c];
-                vfma(acc0, coef[t], b0);
-                vfma(acc1, coef[t + groups], b1);
+            if (rv.tile) {          // resident tile: pointer arithmetic only
+                const VT* p = reinterpret_cast<const VT*>(rv.tile + (size_t)grp * rv.kp) + c;
+                const size_t stride = (size_t)groups * rv.kp / V;
+                for (; t + groups < n; t += 2 * groups) {
+                    const VT b0 = p[0], b1 = p[stride];
+                    vfma(acc0, coef[t], b0);
+                    vfma(acc1, coef[t + groups], b1);
+                    p += 2 * stride;
+                }
+                if (t < n) vfma(acc0, coef[t], p[0]);
+            } else {                // tile in global memory / L2
+                const VT* Fv = reinterpret_cast<const VT*>(rv.F) + c;
+                const size_t ldv = (size_t)rv.ldf / V;
+                for (; t + groups < n; t += 2 * groups) {
+                    const VT b0 = Fv[(size_t)rv.ind[t] * ldv], b1 = Fv[(size_t)rv.ind[t + groups] * ldv];
+                    vfma(acc0, coef[t], b0);
+                    vfma(acc1, coef[t + groups], b1);
+                }
+                if (t < n) vfma(acc0, coef[t], Fv[(size_t)rv.ind[t] * ldv]);
             }
-            if (t < n) vfma(acc0, coef[t], reinterpret_cast<const VT*>(rv.rowp(t))[c]);
             vaddto(acc0, acc1);
         }
         scr[rk] = acc0;
@@ -182,17 +203,35 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
         if (rk < L) {  // group 0 folds the other groups in a fixed order
             VT tot = scr[rk];
             for (int gq = 1; gq < groups; gq++) vaddto(tot, scr[gq * L + rk]);
-            VT base = gv[rk];
-            vaddto(base, tot);
-            gv[rk] = base;
+            if (Team::is_gang) {
+                scr[rk] = tot;   // groups >= 1 here is read by nobody else: safe to overwrite slot rk
+            } else {
+                VT base = gv[rk];
+                vaddto(base, tot);
+                gv[rk] = base;
+            }
         }
     } else {
         for (int c = rk; c < L; c += sz) {
             VT acc;
             vzero(acc);
             for (int t = 0; t < n; t++) vfma(acc, coef[t], reinterpret_cast<const VT*>(rv.rowp(t))[c]);
+            if (Team::is_gang) {
+                scr[c] = acc;    // needs gscr >= ldf reals: guaranteed when L > team size is excluded for gangs
+            } else {
+                VT base = gv[c];
+                vaddto(base, acc);
+                gv[c] = base;
+            }
+        }
+    }
+    if (Team::is_gang) {
+        // fold the per-CTA partial vectors of the cluster, then add onto g
+        tm.sync();
+        tm.nnz_vec_sum(rv.gscr, rv.ldf);
+        for (int c = rk; c < L; c += sz) {
             VT base = gv[c];
-            vaddto(base, acc);
+            vaddto(base, scr[c]);
             gv[c] = base;
         }
     }
@@ -214,7 +253,7 @@ PMF_DEVINL real sum_xlogp(const Team& tm, const RowView<real>& rv, const real* p
     }
     real s = 0;
     for (int t = tm.rank(); t < n; t += tm.size()) s += xlogp(rv.xv[t], p[t]);
-    return tm.sum(s);
+    return tm.nnz_sum(s);
 }
 
 // Constants of one half-sweep's row sub-problems.

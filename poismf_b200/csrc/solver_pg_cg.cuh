@@ -40,11 +40,8 @@ PMF_DEVINL void solve_pg(const Team& tm, const RowView<real>& rv, const HalfSwee
     }
 }
 
-// ---- cg -------------------------------------------------------------------
-// CACHED (fast mode, limit_step only): the line search re-uses p_t = <x,F_t> and
-// q_t = <d,F_t> so that a trial costs O(n) instead of O(n*k) — the optimisation
-// the reference's own TODO describes (src/poismf.c:191-193, nonnegcg.c:291-294).
-template <bool STRICT, bool CACHED, class real, class Team>
+// ---- cg (direct: every objective evaluation re-reads the tile) ---------------
+template <bool STRICT, class real, class Team>
 PMF_DEVINL void solve_cg(const Team& tm, const RowView<real>& rv_in, const HalfSweepConsts<real>& hc,
                          const CgVecs<real>& vv)
 {
@@ -129,38 +126,7 @@ PMF_DEVINL void solve_cg(const Team& tm, const RowView<real>& rv_in, const HalfS
         real step = smax;
         bool accepted = false;
 
-        if (CACHED) {
-            // q_t = <d, F_t> once per CG iteration; p_trial = p + step*q
-            dots<false>(tm, rv, d, rv.pc);
-            for (int ls = 0; ls < max_ls; ls++) {
-                real reg = 0, sq = 0;
-                for (int i = tm.rank(); i < k; i += tm.size()) {
-                    real v = fma(step, d[i], x[i]);
-                    v = ((double)v >= 1e-15) ? v : (real)0;
-                    xnew[i] = v;
-                    reg = fma(csum[i], v, reg);
-                    sq = fma(v, v, sq);
-                }
-                real lsum = 0;
-                for (int t = tm.rank(); t < rv.n; t += tm.size())
-                    lsum += xlogp(rv.xv[t], fma(step, rv.pc[t], rv.pa[t]));
-                reg = tm.sum(reg); sq = tm.sum(sq); lsum = tm.sum(lsum);
-                fnew = fma(hc.l2, sq, reg) - lsum * hc.w;
-                if (!is_bad(fnew) && fnew <= fcur - c_ls * step * dsq) {
-                    tm.sync();
-                    vcopy(tm, xnew, x, k);
-                    for (int t = tm.rank(); t < rv.n; t += tm.size())
-                        rv.pa[t] = fma(step, rv.pc[t], rv.pa[t]);
-                    tm.sync();
-                    accepted = true;
-                    break;
-                }
-                nfe++;
-                if (nfe >= maxnfeval) return;
-                step *= decr;
-                tm.sync();
-            }
-        } else {
+        {
             for (int ls = 0; ls < max_ls; ls++) {                   // :297-327
                 for (int i = tm.rank(); i < k; i += tm.size()) {
                     real v = mad<STRICT>(step, d[i], x[i]);
@@ -189,6 +155,148 @@ PMF_DEVINL void solve_cg(const Team& tm, const RowView<real>& rv_in, const HalfS
         dprev = d; gprev = g;                                      // :335-339
         d = (d == vv.d0) ? vv.d1 : vv.d0;
         g = (g == vv.g0) ? vv.g1 : vv.g0;
+    }
+}
+
+// ---- cg, cached line search (fast numerics, limit_step only) -------------------
+// The line search re-uses p_t = <x,F_t> and q_t = <d,F_t>, so a trial costs O(n) instead of
+// O(n*k) — the optimisation the reference's own TODO describes (src/poismf.c:191-193,
+// nonnegcg.c:291-294); legal with limit_step because the clip then moves a coordinate by
+// less than 1e-15.  Trial steps form the fixed geometric sequence step, step/4, ...: they
+// are evaluated in batches (1, then 4 at a time) with ONE reduction over the non-zeros per
+// batch, and the first acceptable one in sequence order wins, as in the sequential search.
+// k-vector reductions are done redundantly per warp (no barriers); one tile pass for the
+// gradient and one for q per CG iteration.
+template <class real, class Team>
+PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const HalfSweepConsts<real>& hc,
+                                const CgVecs<real>& vv)
+{
+    const int k = rv.k, n = rv.n;
+    const real tol = (real)1e-2, decr = (real)0.25, c_ls = (real)0.01;
+    const int max_ls = 20, maxnfeval = 150;
+    real* x = vv.x;
+    real *g = vv.g0, *d = vv.d0, *gprev = vv.g1, *dprev = vv.d1;
+    const real* csum = vv.csum;
+    const int kb = tm.kbegin(), ks = tm.kstride();
+    const bool kwriter = tm.rank() < ks;          // the first warp / sub-warp stores k-vectors
+    const int maxiter = hc.maxupd <= 0 ? INT32_MAX : hc.maxupd;
+
+    dots<false>(tm, rv, x, rv.pa);                                // p_t = <x, F_t>
+    real fcur;
+    {
+        real ls = 0;
+        for (int t = tm.rank(); t < n; t += tm.size()) ls += xlogp(rv.xv[t], rv.pa[t]);
+        ls = tm.nnz_sum(ls);
+        real reg = 0, sq = 0;
+        for (int i = kb; i < k; i += ks) { const real xi = x[i]; reg = fma(csum[i], xi, reg); sq = fma(xi, xi, sq); }
+        reg = tm.ksum(reg); sq = tm.ksum(sq);
+        fcur = fma(hc.l2, sq, reg) - ls * hc.w;                   // nonnegcg.c:191
+    }
+    if (is_bad(fcur)) return;
+    int nfe = 1;
+    real gprev_sq = 0, fnew = 0;
+
+    for (int it = 0; it < maxiter; it++) {
+        // ---- gradient at x (:231): coefficients, then one pass over the tile
+        for (int t = tm.rank(); t < n; t += tm.size()) rv.pb[t] = -rv.xv[t] / rv.pa[t];
+        if (hc.w == (real)1) {
+            for (int i = tm.rank(); i < k; i += tm.size()) g[i] = fma(hc.two_l2, x[i], csum[i]);
+        } else {
+            for (int i = tm.rank(); i < k; i += tm.size()) g[i] = 0;
+        }
+        tm.sync();
+        gaxpy<false>(tm, rv, rv.pb, g);
+        if (hc.w != (real)1) {
+            for (int i = tm.rank(); i < k; i += tm.size()) g[i] = fma(hc.two_l2, x[i], fma(g[i], hc.w, csum[i]));
+            tm.sync();
+        }
+        // ---- direction (:236-261) and its scalars, redundantly per warp
+        real theta = 0, beta = 0;
+        if (it > 0) {
+            for (int i = kb; i < k; i += ks)
+                if (!(x[i] <= (real)0)) {
+                    const real gi = g[i];
+                    theta = fma(gi, dprev[i], theta);
+                    beta = fma(gi, gi - gprev[i], beta);
+                }
+            theta = tm.ksum(theta) / gprev_sq;
+            beta = tm.ksum(beta) / gprev_sq;
+        }
+        real gd = 0, dsq = 0, gg = 0, m = (real)1;
+        for (int i = kb; i < k; i += ks) {
+            const real xi = x[i], gi = g[i];
+            real di = (xi <= (real)0 && gi >= (real)0) ? (real)0 : -gi;
+            if (it > 0 && !(xi <= (real)0)) di += beta * dprev[i] - theta * (gi - gprev[i]);
+            if (kwriter) d[i] = di;
+            gd = fma(gi, di, gd); dsq = fma(di, di, dsq); gg = fma(gi, gi, gg);
+            if (di < (real)0) { const real r = -xi / di; m = (r < m) ? r : m; }     // limit_step (:272-279)
+        }
+        gd = tm.ksum(gd); dsq = tm.ksum(dsq); gg = tm.ksum(gg);
+        const real smax = tm.kmin(m);
+        tm.sync();                                                 // d visible to everyone
+        if (fabs((double)gd) <= (double)tol) return;               // :264-269
+
+        dots<false>(tm, rv, d, rv.pc);                             // q_t = <d, F_t>
+
+        // ---- line search (:297-327)
+        constexpr int NB = 4;
+        real step = smax;
+        bool accepted = false, stop_all = false;
+        int ls = 0;
+        while (ls < max_ls && !accepted && !stop_all) {
+            const int nb = (ls == 0) ? 1 : ((max_ls - ls) < NB ? (max_ls - ls) : NB);
+            real steps[NB], reg[NB], sq[NB], lsv[NB];
+            {
+                real sj = step;
+#pragma unroll
+                for (int j = 0; j < NB; j++) { steps[j] = sj; sj *= decr; reg[j] = 0; sq[j] = 0; lsv[j] = 0; }
+            }
+            for (int i = kb; i < k; i += ks) {
+                const real xi = x[i], di = d[i], ci = csum[i];
+#pragma unroll
+                for (int j = 0; j < NB; j++) if (j < nb) {
+                    real v = fma(steps[j], di, xi);
+                    v = ((double)v >= 1e-15) ? v : (real)0;
+                    reg[j] = fma(ci, v, reg[j]);
+                    sq[j] = fma(v, v, sq[j]);
+                }
+            }
+            for (int t = tm.rank(); t < n; t += tm.size()) {
+                const real pt = rv.pa[t], qt = rv.pc[t], xt = rv.xv[t];
+#pragma unroll
+                for (int j = 0; j < NB; j++) if (j < nb) lsv[j] += xlogp(xt, fma(steps[j], qt, pt));
+            }
+#pragma unroll
+            for (int j = 0; j < NB; j++) if (j < nb) { reg[j] = tm.ksum(reg[j]); sq[j] = tm.ksum(sq[j]); }
+            tm.nnz_sum_n(lsv);
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                if (j < nb && !accepted && !stop_all) {
+                    fnew = fma(hc.l2, sq[j], reg[j]) - lsv[j] * hc.w;
+                    if (!is_bad(fnew) && fnew <= fcur - c_ls * steps[j] * dsq) {
+                        accepted = true;
+                        step = steps[j];
+                    } else {
+                        nfe++;
+                        if (nfe >= maxnfeval) stop_all = true;
+                    }
+                }
+            }
+            if (!accepted) { step = steps[nb - 1] * decr; ls += nb; }
+        }
+        if (stop_all && !accepted) return;                          // :317-320
+        if (accepted) {
+            for (int i = tm.rank(); i < k; i += tm.size()) {
+                const real v = fma(step, d[i], x[i]);
+                x[i] = ((double)v >= 1e-15) ? v : (real)0;
+            }
+            for (int t = tm.rank(); t < n; t += tm.size()) rv.pa[t] = fma(step, rv.pc[t], rv.pa[t]);
+        }
+        tm.sync();
+        fcur = fnew;                                               // :328 (Q4)
+        gprev_sq = gg;                                             // :332
+        real* tv = d; d = dprev; dprev = tv;                       // :335-339
+        tv = g; g = gprev; gprev = tv;
     }
 }
 

@@ -732,7 +732,7 @@ PMF_DEVINL void solve_tn(const Team& tm, const RowView<real>& rv, const HalfSwee
         PMF_EW(i) prev[i] = prev[i] + (real)(-1.) * x[i];
         tm.sync();
         const real dd = c.dot(prev, prev);
-        if (tm.rank() == 0 && D(dd) <= 1e-4) atomicAdd(n_unchanged, 1ULL);
+        if (tm.rank() == 0 && tm.owns_row() && D(dd) <= 1e-4) atomicAdd(n_unchanged, 1ULL);
     }
 }
 

@@ -103,7 +103,7 @@ def test_fast_llk_gate(dtype, case):
     """FINAL Poisson log-likelihood within 1e-4 relative of the oracle's (north_star) — the stable
     quantity for the solvers whose coordinates are chaotic in the rounding.
     Where the reference itself, rebuilt with FMA contraction and -O3 (oracle/_ref "fast" build),
-    misses that gate against its strict build, the device is held to 3x that noise floor."""
+    misses that gate against its strict build, the device is held to 5x that noise floor."""
     from oracle.oracle import Ref
     csr, csc, A0, B0, k = problem("pl2k", dtype)
     method, kw = hyper(case, k)
@@ -122,7 +122,7 @@ def test_fast_llk_gate(dtype, case):
         A2, B2 = A0.copy(), B0.copy()
         Ref(dtype, fast=True).run_poismf(A2, B2, csr, csc, method, **kw)
         noise = abs(orc.llk(A2, B2, csr) - l_ref) / abs(l_ref)
-        gate = max(gate, 3 * noise)
+        gate = max(gate, 5 * noise)
     elif dtype == np.float32 and method == "tncg":
         gate = 2e-2                 # reference-vs-reference reaches 1.7e-2 in float
     assert abs(l_dev - l_ref) <= gate * abs(l_ref), (l_dev, l_ref, gate)
