@@ -8,10 +8,12 @@
 #include <algorithm>
 #include <atomic>
 #include <csignal>
+#include <ctime>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -156,6 +158,11 @@ template <class real> struct HandleT : pmf_b200_handle {
     int n_partial = 0;
     int* counters = nullptr;    // one per bin
     unsigned long long* d_unchanged = nullptr;
+    // bins of one half-sweep are independent: they are launched on a few side streams so that
+    // small or latency-bound bins overlap (fork from / join to the handle's stream with events)
+    static constexpr int NAUX = 6;
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     static constexpr int V = RealTraits<real>::V;
 
     ~HandleT() override
@@ -168,6 +175,11 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (partial) cudaFree(partial);
         if (counters) cudaFree(counters);
         if (d_unchanged) cudaFree(d_unchanged);
+        for (int i = 0; i < NAUX; i++) {
+            if (aux[i]) cudaStreamDestroy(aux[i]);
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 
@@ -192,6 +204,11 @@ template <class real> struct HandleT : pmf_b200_handle {
         CK(cudaMalloc(&partial, (size_t)n_partial * ldf * sizeof(real)));
         CK(cudaMalloc(&counters, 64 * sizeof(int)));
         CK(cudaMalloc(&d_unchanged, sizeof(unsigned long long)));
+        for (int i = 0; i < NAUX; i++) {
+            CK(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         return 0;
     }
 
@@ -245,21 +262,47 @@ template <class real> struct HandleT : pmf_b200_handle {
         return fail("set_matrix: index_bytes must be 4 or 8");
     }
 
+    // dense host rows are k reals, device rows ldf reals: one contiguous copy + a device repack
+    // (a pitched cudaMemcpy2D of 200-byte rows is ~10x slower over PCIe)
+    int copy_in(real* dev, const void* host, size_t n)
+    {
+        if (ldf == k) { CK(cudaMemcpyAsync(dev, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, stream)); return 0; }
+        real* tmp = nullptr;
+        CK(cudaMalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
+        CK(cudaMemcpyAsync(tmp, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, stream));
+        pad_rows_kernel<real><<<num_sms * 8, 256, 0, stream>>>(tmp, dev, n, k, ldf);
+        LAUNCHED();
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        cudaFree(tmp);
+        return 0;
+    }
+    int copy_out(void* host, const real* dev, size_t n)
+    {
+        if (ldf == k) { CK(cudaMemcpyAsync(host, dev, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, stream)); return 0; }
+        real* tmp = nullptr;
+        CK(cudaMalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
+        unpad_rows_kernel<real><<<num_sms * 8, 256, 0, stream>>>(dev, tmp, n, k, ldf);
+        LAUNCHED();
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host, tmp, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        cudaFree(tmp);
+        return 0;
+    }
     int set_factors(const void* Ah, const void* Bh) override
     {
         CK(cudaSetDevice(device));
-        const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
-        if (Ah) CK(cudaMemcpy2DAsync(A, pitch, Ah, w, w, dimA, cudaMemcpyHostToDevice, stream));
-        if (Bh) CK(cudaMemcpy2DAsync(B, pitch, Bh, w, w, dimB, cudaMemcpyHostToDevice, stream));
+        if (Ah && copy_in(A, Ah, dimA)) return 1;
+        if (Bh && copy_in(B, Bh, dimB)) return 1;
         CK(cudaStreamSynchronize(stream));
         return 0;
     }
     int get_factors(void* Ah, void* Bh) override
     {
         CK(cudaSetDevice(device));
-        const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
-        if (Ah) CK(cudaMemcpy2DAsync(Ah, w, A, pitch, w, dimA, cudaMemcpyDeviceToHost, stream));
-        if (Bh) CK(cudaMemcpy2DAsync(Bh, w, B, pitch, w, dimB, cudaMemcpyDeviceToHost, stream));
+        if (Ah && copy_out(Ah, A, dimA)) return 1;
+        if (Bh && copy_out(Bh, B, dimB)) return 1;
         CK(cudaStreamSynchronize(stream));
         return 0;
     }
@@ -275,7 +318,7 @@ template <class real> struct HandleT : pmf_b200_handle {
     // ---- planner: bin the local rows of one side by non-zero count -------------
     size_t slice_bytes(int team_threads, int nvec, int cap) const
     {
-        size_t b = 288 + (size_t)team_threads * 16 + (size_t)nvec * kp * sizeof(real) +
+        size_t b = 640 + (size_t)team_threads * 16 + (size_t)nvec * kp * sizeof(real) +
                    (size_t)4 * cap * sizeof(real) + (size_t)cap * kp * sizeof(real);
         return round_up_sz(b, 16);
     }
@@ -287,9 +330,26 @@ template <class real> struct HandleT : pmf_b200_handle {
         const int nvec = method == PMF_PG ? 3 : (method == PMF_CG ? 7 : TN_NUM_VECS);
         std::vector<Bin> bins;
         // (sub-)warp-per-row bins: {lanes per row, tile capacity}; sub-warps in fast numerics only
-        const int wdef[4][2] = {{8, 16}, {16, 32}, {32, 64}, {32, 128}};
-        for (int c = 0; c < 4; c++) {
+        // {lanes per row, tile capacity}.  Rows in flight per SM are bounded by shared memory
+        // (tile + solver state per row), so capacities are graded finely; a full warp per row
+        // gives the shortest per-row latency, which is what bounds throughput at that occupancy.
+        int wdef[8][2] = {{16, 16}, {32, 24}, {32, 32}, {32, 48}, {32, 64}, {32, 96}, {32, 128}, {0, 0}};
+        int nw = 7;
+        if (const char* e = getenv("POISMF_B200_WIDTHS")) {   // tuning knob: "w:cap,w:cap,..." (up to 8)
+            nw = 0;
+            const char* q = e;
+            while (*q && nw < 8) {
+                int w = 0, c = 0, used = 0;
+                if (sscanf(q, "%d:%d%n", &w, &c, &used) != 2) break;
+                wdef[nw][0] = w; wdef[nw][1] = c; nw++;
+                q += used;
+                if (*q == ',') q++;
+            }
+        }
+        for (int c = 0; c < nw; c++) {
             const int width = wdef[c][0];
+            if (width != 8 && width != 16 && width != 32) continue;
+            if (c > 0 && wdef[c][1] <= wdef[c - 1][1]) continue;
             if (strict && width < 32) continue;
             Bin b;
             b.block = false; b.cap = wdef[c][1]; b.width = width;
@@ -301,39 +361,43 @@ template <class real> struct HandleT : pmf_b200_handle {
             b.smem = b.slice * (b.threads / width);
             bins.push_back(b);
         }
-        // CTA-per-row bins: largest capacity with 4, 2, 1 resident CTAs per SM
+        // CTA-per-row bins: largest capacity with 4, 2, 1 resident CTAs per SM.  The one-per-SM
+        // bins (and the clusters below) run 512 threads per CTA: their rows are long enough to
+        // feed them, and per-row latency is what bounds these bins.
         const int ctas[3] = {4, 2, 1};
         int last_cap = bins.empty() ? 0 : bins.back().cap;
         for (int c = 0; c < 3; c++) {
+            const int thr = (ctas[c] == 1 && !strict) ? 512 : 256;
             const size_t budget = std::min(SMEM_CTA_MAX, SMEM_PER_SM / ctas[c] - SMEM_CTA_RESERVED);
-            const size_t fixed = slice_bytes(256, nvec, 0) + 16;
+            const size_t fixed = slice_bytes(thr, nvec, 0) + 16;
             if (budget <= fixed) continue;
             int cap = (int)((budget - fixed) / ((size_t)(kp + 4) * sizeof(real)));
             cap = cap / 4 * 4;
             if (cap <= last_cap) continue;
             Bin b;
-            b.block = true; b.cap = cap; b.threads = 256;
-            b.slice = slice_bytes(256, nvec, cap);
+            b.block = true; b.cap = cap; b.threads = thr;
+            b.slice = slice_bytes(thr, nvec, cap);
             b.smem = b.slice;
             bins.push_back(b);
             last_cap = cap;
         }
         if (!strict) {
             // cluster-per-row bins: G CTAs stage G slices of the tile (fast numerics only)
-            const size_t fixed = slice_bytes(256, nvec, 0) + GANG_XBYTES + 16;
+            const int thr = 512;
+            const size_t fixed = slice_bytes(thr, nvec, 0) + GANG_XBYTES + 16;
             int gcap = (int)((SMEM_CTA_MAX - fixed) / ((size_t)(kp + 4) * sizeof(real)));
             gcap = gcap / 4 * 4;
             const int gs[4] = {2, 4, 8, 16};
             for (int c = 0; c < 4 && gcap > 0; c++) {
                 Bin b;
-                b.block = true; b.cluster = gs[c]; b.cap = gcap; b.threads = 256;
-                b.slice = slice_bytes(256, nvec, gcap) + GANG_XBYTES;
+                b.block = true; b.cluster = gs[c]; b.cap = gcap; b.threads = thr;
+                b.slice = slice_bytes(thr, nvec, gcap) + GANG_XBYTES;
                 b.smem = b.slice;
                 bins.push_back(b);
             }
             Bin b;     // beyond 16 resident slices: 16 CTAs, each streaming its slice from L2
-            b.block = true; b.cluster = 16; b.cap = 0; b.threads = 256;
-            b.slice = slice_bytes(256, nvec, 0) + GANG_XBYTES;
+            b.block = true; b.cluster = 16; b.cap = 0; b.threads = thr;
+            b.slice = slice_bytes(thr, nvec, 0) + GANG_XBYTES;
             b.smem = b.slice;
             bins.push_back(b);
         } else {   // strict numerics: everything longer stays on one CTA, tile in global memory / L2
@@ -355,9 +419,22 @@ template <class real> struct HandleT : pmf_b200_handle {
         }
         size_t total = empty.size();
         for (auto& b : bins) {
-            std::stable_sort(b.rows.begin(), b.rows.end(), [&](int a, int c) {
-                return (S.h_ptr[a + 1] - S.h_ptr[a]) > (S.h_ptr[c + 1] - S.h_ptr[c]);
-            });
+            // longest first; counting sort (row lengths inside a bin span a small range)
+            if (b.rows.size() > 1) {
+                const long long mx = b.max_nnz;
+                if (mx <= (1 << 22)) {
+                    std::vector<int> cnt((size_t)mx + 2, 0);
+                    for (int r : b.rows) cnt[(size_t)(mx - (S.h_ptr[r + 1] - S.h_ptr[r])) + 1]++;
+                    for (size_t i = 1; i < cnt.size(); i++) cnt[i] += cnt[i - 1];
+                    std::vector<int> sorted(b.rows.size());
+                    for (int r : b.rows) sorted[(size_t)cnt[(size_t)(mx - (S.h_ptr[r + 1] - S.h_ptr[r]))]++] = r;
+                    b.rows.swap(sorted);
+                } else {
+                    std::stable_sort(b.rows.begin(), b.rows.end(), [&](int a, int c) {
+                        return (S.h_ptr[a + 1] - S.h_ptr[a]) > (S.h_ptr[c + 1] - S.h_ptr[c]);
+                    });
+                }
+            }
             total += b.rows.size();
         }
         CK(cudaMalloc(&S.d_all_rows, std::max<size_t>(total, 1) * sizeof(int)));
@@ -434,6 +511,11 @@ template <class real> struct HandleT : pmf_b200_handle {
         hc.step_w = step * w;
         hc.neg_step = -step;
         hc.cdiv = (real)cdiv_d;
+        {   // (double)v >= 1e-15  <=>  v >= clip_thr  for every finite `real` v
+            real c = (real)1e-15;
+            if ((double)c < 1e-15) c = std::nextafter(c, (real)1);
+            hc.clip_thr = c;
+        }
         hc.maxupd = (int)std::min<size_t>(p.maxupd, (size_t)INT32_MAX);
         hc.limit_step = p.limit_step; hc.reuse_prev = p.reuse_prev;
         hc.early_stop = (p.method == PMF_TNCG && p.early_stop) ? 1 : 0;
@@ -453,9 +535,20 @@ template <class real> struct HandleT : pmf_b200_handle {
         CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
         if (hc.early_stop) CK(cudaMemsetAsync(d_unchanged, 0, sizeof(unsigned long long), stream));
 
+        const bool overlap = !profiling && !getenv("POISMF_B200_SERIAL_BINS");
+        if (overlap) CK(cudaEventRecord(ev_fork, stream));
+        int n_launched = 0;
+        bool used[NAUX] = {};
         for (int bi = (int)S.bins.size() - 1; bi >= 0; bi--) {    // heaviest rows first
             const Bin& b = S.bins[bi];
             if (b.rows.empty()) continue;
+            cudaStream_t ls = stream;
+            if (overlap) {
+                const int si = n_launched % NAUX;
+                ls = aux[si];
+                if (!used[si]) { CK(cudaStreamWaitEvent(ls, ev_fork, 0)); used[si] = true; }
+            }
+            n_launched++;
             SideParams<real> P;
             P.M = M + S.row_begin * (size_t)ldf;
             P.F = F; P.xv = S.xv; P.ptr = S.ptr; P.ind = S.ind; P.csum = csum;
@@ -471,7 +564,7 @@ template <class real> struct HandleT : pmf_b200_handle {
             cfg.cached = !strict && !(p.flags & PMF_FLAG_NO_CACHED);
             cfg.threads = b.threads;
             cfg.smem_bytes = b.smem;
-            cfg.stream = stream;
+            cfg.stream = ls;
             const int teams = b.threads / b.width;
             cfg.needed = b.block ? P.nrows : (P.nrows + teams - 1) / teams;
             cfg.team_width = b.width;
@@ -497,6 +590,12 @@ template <class real> struct HandleT : pmf_b200_handle {
                 S.bins[bi].ev.push_back(ev0); S.bins[bi].ev.push_back(ev1);
             }
         }
+        if (overlap)
+            for (int si = 0; si < NAUX; si++)
+                if (used[si]) {
+                    CK(cudaEventRecord(ev_join[si], aux[si]));
+                    CK(cudaStreamWaitEvent(stream, ev_join[si], 0));
+                }
         if (hc.early_stop && n_unchanged) {
             CK(cudaMemcpyAsync(n_unchanged, d_unchanged, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
@@ -659,7 +758,15 @@ extern "C" int pmf_b200_run_poismf(int dtype, int index_bytes,
         }
     }
     int rc = 0;
+    const bool timing = getenv("POISMF_B200_TIMING") != nullptr;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    double t0 = now(), t1;
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        t1 = now(); fprintf(stderr, "poismf_b200 timing: %-14s %8.2f ms\n", what, t1 - t0); t0 = t1;
+    };
     pmf_b200_handle* h = pmf_b200_create(dtype, dimA, dimB, k, env_device());
+    lap("create");
     if (!h) rc = 1;
     const size_t isz = (size_t)index_bytes;
     auto last = [&](const void* ptr, size_t n) -> size_t {
@@ -667,17 +774,22 @@ extern "C" int pmf_b200_run_poismf(int dtype, int index_bytes,
     };
     if (!rc) rc = h->set_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, last(Xr_indptr, dimA), index_bytes, 0, dimA);
     if (!rc) rc = h->set_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, last(Xc_indptr, dimB), index_bytes, 0, dimB);
+    lap("upload X");
     if (!rc) rc = h->set_factors(A, B);
+    lap("upload A,B");
     if (!rc) {
         pmf_b200_params p;
         p.l2_reg = l2_reg; p.l1_reg = l1_reg; p.w_mult = w_mult; p.step_size = step_size;
         p.method = method; p.limit_step = limit_step; p.numiter = numiter; p.maxupd = maxupd;
         p.early_stop = early_stop; p.reuse_prev = reuse_prev; p.flags = env_flags(flags);
         rc = h->sweeps(p);
+        if (timing) { pmf_b200_sync(h); lap("plan+sweeps"); }
         const int rc2 = (rc != 1) ? h->get_factors(A, B) : 0;   // interrupted fits still return usable factors
         if (rc2) rc = 1;
+        lap("download");
     }
     if (h) pmf_b200_destroy(h);
+    lap("destroy");
     if (rc == 1) fprintf(stderr, "Error: out of memory.\n");
     {
         std::lock_guard<std::mutex> g(g_sig_mutex);

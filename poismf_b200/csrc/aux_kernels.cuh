@@ -36,6 +36,26 @@ template <class real> PMF_DEVINL real colsum_finish(real v, const ColsumFinal<re
     return v;
 }
 
+// dense host layout [n x k]  <->  device layout [n x ldf] (rows padded to 16 bytes, pads zero)
+template <class real>
+__global__ void pad_rows_kernel(const real* __restrict__ dense, real* __restrict__ padded, size_t n, int k, int ldf)
+{
+    const size_t total = n * (size_t)ldf;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / ldf; const int c = (int)(i - r * ldf);
+        padded[i] = c < k ? dense[r * k + c] : (real)0;
+    }
+}
+template <class real>
+__global__ void unpad_rows_kernel(const real* __restrict__ padded, real* __restrict__ dense, size_t n, int k, int ldf)
+{
+    const size_t total = n * (size_t)k;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / k; const int c = (int)(i - r * k);
+        dense[i] = padded[r * ldf + c];
+    }
+}
+
 // Reference order: out[c] = ((M[0,c] + M[1,c]) + M[2,c]) + ...   one thread per column.
 template <class real>
 __global__ void colsum_seq_kernel(const real* __restrict__ M, size_t nrow, int k, int ldf,

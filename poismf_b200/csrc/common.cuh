@@ -143,6 +143,10 @@ template <int W> struct SubWarpTeam {
     template <class T> PMF_DEVINL T ksum(T v) const { return warp_sum(v, mask, W); }
     template <class T> PMF_DEVINL T kmin(T v) const { return warp_min(v, mask, W); }
     template <class T> PMF_DEVINL T kmax(T v) const { return warp_max(v, mask, W); }
+    // the k-scalar phase of the solvers is executed by the "k leader" (here: the whole team)
+    static constexpr bool k_bcast = false;
+    PMF_DEVINL bool k_leader() const { return true; }
+    template <class T> PMF_DEVINL T* kslots() const { return nullptr; }
     static constexpr bool is_gang = false;
     PMF_DEVINL bool owns_row() const { return true; }
     PMF_DEVINL unsigned crank_() const { return 0; }
@@ -158,7 +162,7 @@ template <int W> struct SubWarpTeam {
 using WarpTeam = SubWarpTeam<32>;
 
 // CTA-level reductions shared by BlockTeam and ClusterTeam.  `red` = 34 doubles of shared
-// memory.  Second stage by shuffles: no serial fold, same bits on every thread.
+// memory (64 slots used by sum_n as floats/doubles... sized below).  Second stage by shuffles.
 struct BlockOps {
     double* red;
     PMF_DEVINL int rank() const { return threadIdx.x; }
@@ -169,7 +173,12 @@ struct BlockOps {
     template <class T> PMF_DEVINL T ksum(T v) const { return warp_sum(v); }
     template <class T> PMF_DEVINL T kmin(T v) const { return warp_min(v); }
     template <class T> PMF_DEVINL T kmax(T v) const { return warp_max(v); }
-    // up to 4 sums at once with one pair of barriers (blockDim <= 256)
+    // the k-scalar phase of the solvers runs on warp 0 only; its results are broadcast through
+    // 12 shared slots (bytes 544..640 of the team scratch) and one barrier
+    static constexpr bool k_bcast = true;
+    PMF_DEVINL bool k_leader() const { return threadIdx.x < 32; }
+    template <class T> PMF_DEVINL T* kslots() const { return reinterpret_cast<T*>(red + 68); }
+    // up to 4 sums at once with one pair of barriers (blockDim <= 512: at most 16 warps)
     template <class T, int N> PMF_DEVINL void sum_n(T (&v)[N]) const
     {
         static_assert(N <= 4, "at most 4 values per block reduction");
@@ -180,15 +189,20 @@ struct BlockOps {
         __syncthreads();   // protect `red` against the previous reduction's readers
         if (lane == 0)
 #pragma unroll
-            for (int j = 0; j < N; j++) r[j * 8 + w] = v[j];
+            for (int j = 0; j < N; j++) r[j * 16 + w] = v[j];
         __syncthreads();
-        // lane l = j*8 + w holds one partial; fold the 8-lane groups with shuffles
-        T part = ((lane & 7) < nw && (lane >> 3) < N) ? r[lane] : (T)0;
-        part += __shfl_xor_sync(0xffffffffu, part, 4);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        // slot j*16 + w; lane l folds slots l (values 0,1) and l+32 (values 2,3) in 16-lane groups
+        T p0 = ((lane & 15) < nw && (lane >> 4) < N) ? r[lane] : (T)0;
+        T p1 = (N > 2 && (lane & 15) < nw && 2 + (lane >> 4) < N) ? r[lane + 32] : (T)0;
 #pragma unroll
-        for (int j = 0; j < N; j++) v[j] = __shfl_sync(0xffffffffu, part, j * 8);
+        for (int o = 8; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            if (N > 2) p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+        }
+        v[0] = __shfl_sync(0xffffffffu, p0, 0);
+        if (N > 1) v[1] = __shfl_sync(0xffffffffu, p0, 16);
+        if (N > 2) v[2] = __shfl_sync(0xffffffffu, p1, 0);
+        if (N > 3) v[3] = __shfl_sync(0xffffffffu, p1, 16);
     }
     template <class T> PMF_DEVINL T sum(T v) const
     {
@@ -205,7 +219,8 @@ struct BlockOps {
         __syncthreads();
         if (lane == 0) r[w] = v;
         __syncthreads();
-        T part = r[(lane & 7) < nw ? (lane & 7) : 0];
+        T part = r[(lane & 15) < nw ? (lane & 15) : 0];
+        part = op(part, __shfl_xor_sync(0xffffffffu, part, 8));
         part = op(part, __shfl_xor_sync(0xffffffffu, part, 4));
         part = op(part, __shfl_xor_sync(0xffffffffu, part, 2));
         part = op(part, __shfl_xor_sync(0xffffffffu, part, 1));
@@ -217,9 +232,9 @@ struct BlockOps {
     {
         T* r = (T*)red;
         __syncthreads();
-        if (threadIdx.x == 0) r[33] = v;
+        if (threadIdx.x == 0) r[66] = v;
         __syncthreads();
-        return r[33];
+        return r[66];
     }
 };
 

@@ -10,6 +10,12 @@
 #include "solver_pg_cg.cuh"
 #include "solver_tn.cuh"
 
+// minimum resident CTAs the (sub-)warp kernels are compiled for: caps registers at 80/thread
+// so that three 256-thread CTAs fit an SM when their shared-memory slices allow it
+#ifndef PMF_WARP_KERNEL_MIN_CTAS
+#define PMF_WARP_KERNEL_MIN_CTAS 3
+#endif
+
 namespace pmf {
 
 template <class real> struct SideParams {
@@ -37,7 +43,7 @@ PMF_DEVINL int num_vecs(int method)
 }
 
 // Shared-memory slice of one team:
-//   [team scratch 288 B][cluster exchange 2*272*8 B (gangs only)][gscr team*16 B][vectors NV*kp]
+//   [team scratch 640 B][cluster exchange 2*272*8 B (gangs only)][gscr team*16 B][vectors NV*kp]
 //   [xv,pa,pb,pc: 4*cap][tile cap*kp]
 constexpr int GANG_XBYTES = 2 * GANG_XSLOTS * 8;
 template <class real> struct Slice {
@@ -49,7 +55,7 @@ template <class real> struct Slice {
     real* tile;
     PMF_DEVINL Slice(unsigned char* base, int team_size, int nvec, int kp, int cap, bool gang = false)
     {
-        team_scratch = base; base += 288;
+        team_scratch = base; base += 640;
         xchg = base; if (gang) base += GANG_XBYTES;
         gscr = (real*)base; base += (size_t)team_size * 16;
         vecs = (real*)base; base += (size_t)nvec * kp * sizeof(real);
@@ -122,7 +128,7 @@ PMF_DEVINL void process_row(const Team& tm, const SideParams<real>& P, const Sli
 // warp).  Each team owns one slice of the CTA's dynamic shared memory and fetches rows from
 // the bin's list through an atomic counter.
 template <class real, int METHOD, bool STRICT, bool CACHED, int W>
-__global__ void __launch_bounds__(256) rows_warp_kernel(const SideParams<real> P)
+__global__ void __launch_bounds__(256, PMF_WARP_KERNEL_MIN_CTAS) rows_warp_kernel(const SideParams<real> P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int team_id = threadIdx.x / W;
@@ -137,8 +143,9 @@ __global__ void __launch_bounds__(256) rows_warp_kernel(const SideParams<real> P
     }
 }
 
-template <class real, int METHOD, bool STRICT, bool CACHED>
-__global__ void __launch_bounds__(256) rows_block_kernel(const SideParams<real> P)
+// THREADS = 256 (several CTAs per SM: registers capped at 80) or 512 (one CTA per SM)
+template <class real, int METHOD, bool STRICT, bool CACHED, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) rows_block_kernel(const SideParams<real> P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int next_row;
@@ -156,19 +163,26 @@ __global__ void __launch_bounds__(256) rows_block_kernel(const SideParams<real> 
 }
 
 // One thread-block cluster per heavy row (fast numerics only: the cross-CTA fold changes
-// the summation order).  Rows are dealt round-robin to the clusters, longest first.
+// the summation order).  Clusters draw rows from the bin's list, longest first.
 template <class real, int METHOD, bool CACHED>
-__global__ void __launch_bounds__(256) rows_cluster_kernel(const SideParams<real> P)
+__global__ void __launch_bounds__(512, 1) rows_cluster_kernel(const SideParams<real> P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cl = cg::this_cluster();
     Slice<real> S(smem, blockDim.x, num_vecs(METHOD), P.kp, P.cap, true);
     ClusterTeam tm(S.team_scratch, S.xchg);
-    const int csize = (int)cl.num_blocks();
-    const int cluster_id = blockIdx.x / csize, nclusters = gridDim.x / csize;
+    __shared__ int next_row;
     real* gs = P.gscratch ? P.gscratch + (size_t)blockIdx.x * 3 * P.gs_stride : nullptr;
-    for (int idx = cluster_id; idx < P.nrows; idx += nclusters)
+    int* leader_slot = cl.map_shared_rank(&next_row, 0);
+    for (;;) {
+        // the cluster's rank-0 CTA draws the next row (longest first); peers read it over DSMEM
+        if (cl.block_rank() == 0 && threadIdx.x == 0) next_row = atomicAdd(P.counter, 1);
+        cl.sync();
+        const int idx = *leader_slot;
+        cl.sync();
+        if (idx >= P.nrows) break;
         process_row<real, METHOD, false, CACHED>(tm, P, S, P.rows[idx], gs);
+    }
     cl.sync();   // nobody leaves while a peer may still read its shared memory
 }
 

@@ -98,6 +98,92 @@ PMF_DEVINL void stage_tile(const Team& tm, const real* __restrict__ F, const int
     tm.sync();
 }
 
+// Fast-mode dot products: lane `rank` handles non-zeros rank, rank+sz, ... NR at a time.
+template <int NR, class real>
+PMF_DEVINL void dots_fast(const RowView<real>& rv, const real* a, real* out, int rank, int sz)
+{
+    using VT = typename Vec16<real>::type;
+    constexpr int V = RealTraits<real>::V;
+    const int n = rv.n, nv = rv.ldf / V;
+    const VT* av = reinterpret_cast<const VT*>(a);
+    for (int t = rank; t < n; t += NR * sz) {
+        const VT* r[NR];
+        if (rv.tile) {       // staged tile: shared-memory addressing only (row t at tile + t*kp)
+            const VT* tv = reinterpret_cast<const VT*>(rv.tile);
+            const int kpv = rv.kp / V;
+#pragma unroll
+            for (int j = 0; j < NR; j++) r[j] = tv + ((t + j * sz < n) ? (t + j * sz) : t) * kpv;
+            real s[NR];
+#pragma unroll
+            for (int j = 0; j < NR; j++) s[j] = 0;
+#pragma unroll 2
+            for (int c = 0; c < nv; c++) {
+                const VT x = av[c];
+#pragma unroll
+                for (int j = 0; j < NR; j++) s[j] = vdot4(x, r[j][c], s[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NR; j++) if (t + j * sz < n) out[t + j * sz] = s[j];
+        } else {             // tile in global memory / L2
+            const VT* Fv = reinterpret_cast<const VT*>(rv.F);
+            const size_t ldv = (size_t)rv.ldf / V;
+#pragma unroll
+            for (int j = 0; j < NR; j++) r[j] = Fv + (size_t)rv.ind[(t + j * sz < n) ? (t + j * sz) : t] * ldv;
+            real s[NR];
+#pragma unroll
+            for (int j = 0; j < NR; j++) s[j] = 0;
+#pragma unroll 2
+            for (int c = 0; c < nv; c++) {
+                const VT x = av[c];
+#pragma unroll
+                for (int j = 0; j < NR; j++) s[j] = vdot4(x, __ldg(r[j] + c), s[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NR; j++) if (t + j * sz < n) out[t + j * sz] = s[j];
+        }
+    }
+}
+
+// Fast-mode dot products for a tile that is NOT staged (rows streamed from global memory / L2):
+// a group of G lanes reads one factor row with coalesced 16-byte loads (lane c takes chunk c),
+// keeps its chunk(s) of `a` in registers, and the G partial sums are folded with shuffles.
+template <class real, class Team>
+PMF_DEVINL void dots_stream(const Team& tm, const RowView<real>& rv, const real* a, real* out)
+{
+    using VT = typename Vec16<real>::type;
+    constexpr int V = RealTraits<real>::V;
+    const int n = rv.n, L = rv.ldf / V;
+    int G = 1;
+    while (G < L && G < 32) G <<= 1;
+    const int lane = threadIdx.x & 31, c = lane & (G - 1);
+    const int gid = tm.rank() / G, ngroups = tm.size() / G;
+    const VT* av = reinterpret_cast<const VT*>(a);
+    const VT* Fv = reinterpret_cast<const VT*>(rv.F);
+    const size_t ldv = (size_t)rv.ldf / V;
+    VT zero; vzero(zero);
+    const bool has0 = c < L, has1 = c + 32 < L;         // second chunk only when L > 32 (G == 32)
+    const VT a0 = has0 ? av[c] : zero, a1 = has1 ? av[c + 32] : zero;
+    // warp-uniform trip count (the shuffles below need every lane of the warp): iterate on the
+    // warp's first group and predicate the memory accesses
+    const int gpw = 32 / G;                                     // groups per warp
+    const int sub = lane / G;
+    for (int base = (tm.rank() >> 5) * gpw; base < n; base += 2 * ngroups) {
+        const int t = base + sub, t2 = t + ngroups;
+        const bool one = t < n, two = t2 < n;
+        const VT* r0 = Fv + (size_t)rv.ind[one ? t : 0] * ldv;
+        const VT* r1 = Fv + (size_t)rv.ind[two ? t2 : 0] * ldv;
+        real s0 = 0, s1 = 0;
+        if (has0) { s0 = vdot4(a0, __ldg(r0 + c), s0); s1 = vdot4(a0, __ldg(r1 + c), s1); }
+        if (has1) { s0 = vdot4(a1, __ldg(r0 + c + 32), s0); s1 = vdot4(a1, __ldg(r1 + c + 32), s1); }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (c == 0) { if (one) out[t] = s0; if (two) out[t2] = s1; }
+    }
+    (void)gid;
+}
+
 // out[t] = <a, F_t>  for every non-zero t of the row.  `a` is a shared-memory
 // vector of kp reals whose pads [k, kp) are zero.
 template <bool STRICT, class real, class Team>
@@ -113,32 +199,12 @@ PMF_DEVINL void dots(const Team& tm, const RowView<real>& rv, const real* a, rea
             out[t] = s;
         }
     } else {
-        using VT = typename Vec16<real>::type;
-        constexpr int V = RealTraits<real>::V;
-        const int nv = rv.ldf / V;
-        const VT* av = reinterpret_cast<const VT*>(a);
         const int sz = tm.size();
-        for (int t = tm.rank(); t < n; t += 4 * sz) {
-            // four non-zeros per lane share each load of `a`
-            const int t1 = t + sz, t2 = t + 2 * sz, t3 = t + 3 * sz;
-            const VT* r0 = reinterpret_cast<const VT*>(rv.rowp(t));
-            const VT* r1 = t1 < n ? reinterpret_cast<const VT*>(rv.rowp(t1)) : r0;
-            const VT* r2 = t2 < n ? reinterpret_cast<const VT*>(rv.rowp(t2)) : r0;
-            const VT* r3 = t3 < n ? reinterpret_cast<const VT*>(rv.rowp(t3)) : r0;
-            real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll 2
-            for (int c = 0; c < nv; c++) {
-                const VT x = av[c];
-                s0 = vdot4(x, r0[c], s0);
-                s1 = vdot4(x, r1[c], s1);
-                s2 = vdot4(x, r2[c], s2);
-                s3 = vdot4(x, r3[c], s3);
-            }
-            out[t] = s0;
-            if (t1 < n) out[t1] = s1;
-            if (t2 < n) out[t2] = s2;
-            if (t3 < n) out[t3] = s3;
-        }
+        if (!rv.tile && sz >= 32) { dots_stream(tm, rv, a, out); tm.sync(); return; }
+        // rows per lane and pass: as many as the row has, up to 4 (they share each load of `a`)
+        if (n <= sz) dots_fast<1>(rv, a, out, tm.rank(), sz);
+        else if (n <= 2 * sz) dots_fast<2>(rv, a, out, tm.rank(), sz);
+        else dots_fast<4>(rv, a, out, tm.rank(), sz);
     }
     tm.sync();
 }
@@ -177,8 +243,8 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
         if (grp < groups) {
             int t = grp;
             if (rv.tile) {          // resident tile: pointer arithmetic only
-                const VT* p = reinterpret_cast<const VT*>(rv.tile + (size_t)grp * rv.kp) + c;
-                const size_t stride = (size_t)groups * rv.kp / V;
+                const VT* p = reinterpret_cast<const VT*>(rv.tile) + grp * (rv.kp / V) + c;
+                const int stride = groups * (rv.kp / V);
                 for (; t + groups < n; t += 2 * groups) {
                     const VT b0 = p[0], b1 = p[stride];
                     vfma(acc0, coef[t], b0);
@@ -190,11 +256,11 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
                 const VT* Fv = reinterpret_cast<const VT*>(rv.F) + c;
                 const size_t ldv = (size_t)rv.ldf / V;
                 for (; t + groups < n; t += 2 * groups) {
-                    const VT b0 = Fv[(size_t)rv.ind[t] * ldv], b1 = Fv[(size_t)rv.ind[t + groups] * ldv];
+                    const VT b0 = __ldg(Fv + (size_t)rv.ind[t] * ldv), b1 = __ldg(Fv + (size_t)rv.ind[t + groups] * ldv);
                     vfma(acc0, coef[t], b0);
                     vfma(acc1, coef[t + groups], b1);
                 }
-                if (t < n) vfma(acc0, coef[t], Fv[(size_t)rv.ind[t] * ldv]);
+                if (t < n) vfma(acc0, coef[t], __ldg(Fv + (size_t)rv.ind[t] * ldv));
             }
             vaddto(acc0, acc1);
         }
@@ -212,16 +278,38 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
             }
         }
     } else {
-        for (int c = rk; c < L; c += sz) {
-            VT acc;
-            vzero(acc);
-            for (int t = 0; t < n; t++) vfma(acc, coef[t], reinterpret_cast<const VT*>(rv.rowp(t))[c]);
-            if (Team::is_gang) {
-                scr[c] = acc;    // needs gscr >= ldf reals: guaranteed when L > team size is excluded for gangs
+        // fewer lanes than 16-byte chunks: each lane owns chunks rk, rk+sz, ... and walks all t
+        for (int c0 = rk; c0 < L; c0 += 2 * sz) {
+            const int c1 = c0 + sz;
+            const bool two = c1 < L;
+            VT acc0, acc1;
+            vzero(acc0); vzero(acc1);
+            if (rv.tile) {
+                const VT* p = reinterpret_cast<const VT*>(rv.tile) + c0;
+                const int kpv = rv.kp / V, off1 = two ? sz : 0;
+                for (int t = 0; t < n; t++, p += kpv) {
+                    const real ct = coef[t];
+                    vfma(acc0, ct, p[0]);
+                    vfma(acc1, ct, p[off1]);
+                }
             } else {
-                VT base = gv[c];
-                vaddto(base, acc);
-                gv[c] = base;
+                const VT* Fv = reinterpret_cast<const VT*>(rv.F);
+                const size_t ldv = (size_t)rv.ldf / V;
+                for (int t = 0; t < n; t++) {
+                    const VT* p = Fv + (size_t)rv.ind[t] * ldv;
+                    const real ct = coef[t];
+                    vfma(acc0, ct, __ldg(p + c0));
+                    if (two) vfma(acc1, ct, __ldg(p + c1));
+                }
+            }
+            if (Team::is_gang) {
+                scr[c0] = acc0;
+                if (two) scr[c1] = acc1;
+            } else {
+                VT base = gv[c0];
+                vaddto(base, acc0);
+                gv[c0] = base;
+                if (two) { VT b1 = gv[c1]; vaddto(b1, acc1); gv[c1] = b1; }
             }
         }
     }
@@ -265,6 +353,7 @@ template <class real> struct HalfSweepConsts {
     real step_w;    // pg: step_size * w_mult      (:151)
     real neg_step;  // pg: -step_size              (:460,:533)
     real cdiv;      // pg: 1/(1+2*l2*step)         (:511)
+    real clip_thr;  // smallest `real` v with (double)v >= 1e-15: the cg clip of nonnegcg.c:303 in `real` arithmetic
     int maxupd;
     int limit_step, reuse_prev, early_stop;
     int method;

@@ -178,7 +178,6 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
     real *g = vv.g0, *d = vv.d0, *gprev = vv.g1, *dprev = vv.d1;
     const real* csum = vv.csum;
     const int kb = tm.kbegin(), ks = tm.kstride();
-    const bool kwriter = tm.rank() < ks;          // the first warp / sub-warp stores k-vectors
     const int maxiter = hc.maxupd <= 0 ? INT32_MAX : hc.maxupd;
 
     dots<false>(tm, rv, x, rv.pa);                                // p_t = <x, F_t>
@@ -210,85 +209,99 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
             for (int i = tm.rank(); i < k; i += tm.size()) g[i] = fma(hc.two_l2, x[i], fma(g[i], hc.w, csum[i]));
             tm.sync();
         }
-        // ---- direction (:236-261) and its scalars, redundantly per warp
-        real theta = 0, beta = 0;
-        if (it > 0) {
-            for (int i = kb; i < k; i += ks)
-                if (!(x[i] <= (real)0)) {
-                    const real gi = g[i];
-                    theta = fma(gi, dprev[i], theta);
-                    beta = fma(gi, gi - gprev[i], beta);
-                }
-            theta = tm.ksum(theta) / gprev_sq;
-            beta = tm.ksum(beta) / gprev_sq;
+        // ---- direction (:236-261) and every k-scalar of this iteration.  Executed by the k
+        // leader (the whole (sub-)warp team, or warp 0 of a CTA team, which then broadcasts).
+        // Besides <g,d>, |d|^2, |g|^2 and the step bound it collects the dot products from which
+        // the regulariser of every trial point follows in O(1):
+        //   <csum, x+s d> = cx + s cd,   |x+s d|^2 = xx + 2 s xd + s^2 dd
+        // (the clip at 1e-15 moves these by < 1e-15 |csum|: inside the cached search's tolerance)
+        real gd = 0, dsq = 0, gg = 0, smax = (real)1, cx = 0, cd = 0, xx = 0, xd = 0;
+        if (tm.k_leader()) {
+            real theta = 0, beta = 0;
+            if (it > 0) {
+                for (int i = kb; i < k; i += ks)
+                    if (!(x[i] <= (real)0)) {
+                        const real gi = g[i];
+                        theta = fma(gi, dprev[i], theta);
+                        beta = fma(gi, gi - gprev[i], beta);
+                    }
+                theta = tm.ksum(theta) / gprev_sq;
+                beta = tm.ksum(beta) / gprev_sq;
+            }
+            real m = (real)1;
+            for (int i = kb; i < k; i += ks) {
+                const real xi = x[i], gi = g[i], ci = csum[i];
+                real di = (xi <= (real)0 && gi >= (real)0) ? (real)0 : -gi;
+                if (it > 0 && !(xi <= (real)0)) di += beta * dprev[i] - theta * (gi - gprev[i]);
+                d[i] = di;
+                gd = fma(gi, di, gd); dsq = fma(di, di, dsq); gg = fma(gi, gi, gg);
+                cx = fma(ci, xi, cx); cd = fma(ci, di, cd); xx = fma(xi, xi, xx); xd = fma(xi, di, xd);
+                if (di < (real)0) { const real r = -xi / di; m = (r < m) ? r : m; }  // limit_step (:272-279)
+            }
+            gd = tm.ksum(gd); dsq = tm.ksum(dsq); gg = tm.ksum(gg);
+            cx = tm.ksum(cx); cd = tm.ksum(cd); xx = tm.ksum(xx); xd = tm.ksum(xd);
+            smax = tm.kmin(m);
+            if (Team::k_bcast && kb == 0) {
+                real* ksl = tm.template kslots<real>();
+                ksl[0] = gd; ksl[1] = dsq; ksl[2] = gg; ksl[3] = cx; ksl[4] = cd; ksl[5] = xx; ksl[6] = xd; ksl[7] = smax;
+            }
         }
-        real gd = 0, dsq = 0, gg = 0, m = (real)1;
-        for (int i = kb; i < k; i += ks) {
-            const real xi = x[i], gi = g[i];
-            real di = (xi <= (real)0 && gi >= (real)0) ? (real)0 : -gi;
-            if (it > 0 && !(xi <= (real)0)) di += beta * dprev[i] - theta * (gi - gprev[i]);
-            if (kwriter) d[i] = di;
-            gd = fma(gi, di, gd); dsq = fma(di, di, dsq); gg = fma(gi, gi, gg);
-            if (di < (real)0) { const real r = -xi / di; m = (r < m) ? r : m; }     // limit_step (:272-279)
+        tm.sync();                                                 // d (and the scalars) visible to everyone
+        if (Team::k_bcast) {
+            const real* ksl = tm.template kslots<real>();
+            gd = ksl[0]; dsq = ksl[1]; gg = ksl[2]; cx = ksl[3]; cd = ksl[4]; xx = ksl[5]; xd = ksl[6]; smax = ksl[7];
         }
-        gd = tm.ksum(gd); dsq = tm.ksum(dsq); gg = tm.ksum(gg);
-        const real smax = tm.kmin(m);
-        tm.sync();                                                 // d visible to everyone
         if (fabs((double)gd) <= (double)tol) return;               // :264-269
 
         dots<false>(tm, rv, d, rv.pc);                             // q_t = <d, F_t>
 
-        // ---- line search (:297-327)
-        constexpr int NB = 4;
+        // ---- line search (:297-327): first trial alone, then four at a time
         real step = smax;
-        bool accepted = false, stop_all = false;
-        int ls = 0;
-        while (ls < max_ls && !accepted && !stop_all) {
-            const int nb = (ls == 0) ? 1 : ((max_ls - ls) < NB ? (max_ls - ls) : NB);
-            real steps[NB], reg[NB], sq[NB], lsv[NB];
+        bool accepted = false;
+        auto freg = [&](real sj) {   // <csum,x'> + l2 |x'|^2 at x' = x + sj d
+            return fma(hc.l2, fma(sj, fma(sj, dsq, xd + xd), xx), fma(sj, cd, cx));
+        };
+        {
+            real lsum = 0;
+            for (int t = tm.rank(); t < n; t += tm.size())
+                lsum += xlogp(rv.xv[t], fma(step, rv.pc[t], rv.pa[t]));
+            lsum = tm.nnz_sum(lsum);
+            fnew = freg(step) - lsum * hc.w;
+            if (!is_bad(fnew) && fnew <= fcur - c_ls * step * dsq) accepted = true;
+            else { nfe++; if (nfe >= maxnfeval) return; }
+        }
+        int ls = 1;
+        while (!accepted && ls < max_ls) {
+            constexpr int NB = 4;
+            const int nb = (max_ls - ls) < NB ? (max_ls - ls) : NB;
+            real steps[NB], lsv[NB];
             {
-                real sj = step;
+                real sj = step * decr;
 #pragma unroll
-                for (int j = 0; j < NB; j++) { steps[j] = sj; sj *= decr; reg[j] = 0; sq[j] = 0; lsv[j] = 0; }
-            }
-            for (int i = kb; i < k; i += ks) {
-                const real xi = x[i], di = d[i], ci = csum[i];
-#pragma unroll
-                for (int j = 0; j < NB; j++) if (j < nb) {
-                    real v = fma(steps[j], di, xi);
-                    v = ((double)v >= 1e-15) ? v : (real)0;
-                    reg[j] = fma(ci, v, reg[j]);
-                    sq[j] = fma(v, v, sq[j]);
-                }
+                for (int j = 0; j < NB; j++) { steps[j] = sj; sj *= decr; lsv[j] = 0; }
             }
             for (int t = tm.rank(); t < n; t += tm.size()) {
                 const real pt = rv.pa[t], qt = rv.pc[t], xt = rv.xv[t];
 #pragma unroll
-                for (int j = 0; j < NB; j++) if (j < nb) lsv[j] += xlogp(xt, fma(steps[j], qt, pt));
+                for (int j = 0; j < NB; j++) lsv[j] += xlogp(xt, fma(steps[j], qt, pt));
             }
-#pragma unroll
-            for (int j = 0; j < NB; j++) if (j < nb) { reg[j] = tm.ksum(reg[j]); sq[j] = tm.ksum(sq[j]); }
             tm.nnz_sum_n(lsv);
+            bool stop_all = false;
 #pragma unroll
             for (int j = 0; j < NB; j++) {
                 if (j < nb && !accepted && !stop_all) {
-                    fnew = fma(hc.l2, sq[j], reg[j]) - lsv[j] * hc.w;
-                    if (!is_bad(fnew) && fnew <= fcur - c_ls * steps[j] * dsq) {
-                        accepted = true;
-                        step = steps[j];
-                    } else {
-                        nfe++;
-                        if (nfe >= maxnfeval) stop_all = true;
-                    }
+                    fnew = freg(steps[j]) - lsv[j] * hc.w;
+                    if (!is_bad(fnew) && fnew <= fcur - c_ls * steps[j] * dsq) { accepted = true; step = steps[j]; }
+                    else { nfe++; if (nfe >= maxnfeval) stop_all = true; }
                 }
             }
-            if (!accepted) { step = steps[nb - 1] * decr; ls += nb; }
+            if (stop_all && !accepted) return;                      // :317-320
+            if (!accepted) { step = steps[nb - 1]; ls += nb; }
         }
-        if (stop_all && !accepted) return;                          // :317-320
         if (accepted) {
             for (int i = tm.rank(); i < k; i += tm.size()) {
                 const real v = fma(step, d[i], x[i]);
-                x[i] = ((double)v >= 1e-15) ? v : (real)0;
+                x[i] = (v >= hc.clip_thr) ? v : (real)0;
             }
             for (int t = tm.rank(); t < n; t += tm.size()) rv.pa[t] = fma(step, rv.pc[t], rv.pa[t]);
         }

@@ -4,6 +4,9 @@
 // kernels build in parallel with the pg/cg ones.
 //   PMF_INST_STRICT : 0/1      PMF_INST_TN : 0 (pg + cg) / 1 (tncg)
 #pragma once
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "kernels.cuh"
 #include "launch.h"
 
@@ -11,39 +14,71 @@ namespace pmf {
 
 // Persistent grid: as many CTAs as can be resident (SMs x occupancy), never more
 // than there are rows to hand out.
+// occupancy queries (and the attribute calls that go with them) are cached per
+// (kernel, block size, shared bytes, cluster size): they cost far more than a launch
+static std::mutex g_occ_mutex;
+static std::map<std::tuple<const void*, int, size_t, int>, int> g_occ_cache;
+
 template <class K> static int persistent_grid(K kern, const LaunchCfg& cfg)
 {
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cfg.threads, cfg.smem_bytes) != cudaSuccess || occ < 1)
-        occ = 1;
+    {
+        std::lock_guard<std::mutex> lk(g_occ_mutex);
+        auto key = std::make_tuple((const void*)kern, cfg.threads, cfg.smem_bytes, 1);
+        auto it = g_occ_cache.find(key);
+        if (it != g_occ_cache.end()) occ = it->second;
+        else {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cfg.threads, cfg.smem_bytes) != cudaSuccess || occ < 1)
+                occ = 1;
+            g_occ_cache[key] = occ;
+        }
+    }
     long long g = (long long)cfg.num_sms * occ;
     if (g > cfg.needed) g = cfg.needed;
     if (g > cfg.max_grid) g = cfg.max_grid;
     return g < 1 ? 1 : (int)g;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize): the attribute is a per-kernel maximum, so
+// it is only ever raised (bins of different tile capacity share one kernel)
+template <class K> static cudaError_t ensure_smem(K kern, size_t bytes)
+{
+    static std::map<const void*, size_t> current;
+    std::lock_guard<std::mutex> lk(g_occ_mutex);
+    auto it = current.find((const void*)kern);
+    if (it != current.end() && it->second >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) current[(const void*)kern] = bytes;
+    return e;
+}
+
 template <class real, int METHOD, bool STRICT, bool CACHED>
 static cudaError_t launch_one(const LaunchCfg& cfg, const SideParams<real>& P)
 {
     cudaError_t e;
-    if (cfg.block_team) {
-        auto kern = rows_block_kernel<real, METHOD, STRICT, CACHED>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+    if (cfg.block_team && cfg.threads == 512 && !STRICT) {
+        auto kern = rows_block_kernel<real, METHOD, STRICT, CACHED, STRICT ? 256 : 512>;
+        e = ensure_smem(kern, cfg.smem_bytes);
+        if (e != cudaSuccess) return e;
+        kern<<<persistent_grid(kern, cfg), cfg.threads, cfg.smem_bytes, cfg.stream>>>(P);
+    } else if (cfg.block_team) {
+        auto kern = rows_block_kernel<real, METHOD, STRICT, CACHED, 256>;
+        e = ensure_smem(kern, cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<persistent_grid(kern, cfg), cfg.threads, cfg.smem_bytes, cfg.stream>>>(P);
     } else if (!STRICT && cfg.team_width == 8) {
         auto kern = rows_warp_kernel<real, METHOD, STRICT, CACHED, STRICT ? 32 : 8>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+        e = ensure_smem(kern, cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<persistent_grid(kern, cfg), cfg.threads, cfg.smem_bytes, cfg.stream>>>(P);
     } else if (!STRICT && cfg.team_width == 16) {
         auto kern = rows_warp_kernel<real, METHOD, STRICT, CACHED, STRICT ? 32 : 16>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+        e = ensure_smem(kern, cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<persistent_grid(kern, cfg), cfg.threads, cfg.smem_bytes, cfg.stream>>>(P);
     } else {
         auto kern = rows_warp_kernel<real, METHOD, STRICT, CACHED, 32>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+        e = ensure_smem(kern, cfg.smem_bytes);
         if (e != cudaSuccess) return e;
         kern<<<persistent_grid(kern, cfg), cfg.threads, cfg.smem_bytes, cfg.stream>>>(P);
     }
@@ -56,22 +91,35 @@ template <class real, int METHOD, bool CACHED>
 static cudaError_t launch_gang_one(const LaunchCfg& cfg, const SideParams<real>& P)
 {
     auto kern = rows_cluster_kernel<real, METHOD, CACHED>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+    cudaError_t e = ensure_smem(kern, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
-    if (cfg.cluster > 8) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
-    }
     cudaLaunchConfig_t lc = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cfg.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
     lc.blockDim = dim3(cfg.threads); lc.dynamicSmemBytes = cfg.smem_bytes; lc.stream = cfg.stream;
-    lc.gridDim = dim3(cfg.cluster);   // placeholder for the occupancy query
     int nclusters = 0;
-    e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &lc);
-    if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); nclusters = cfg.num_sms / cfg.cluster / 2; if (nclusters < 1) nclusters = 1; }
+    {
+        std::lock_guard<std::mutex> lk(g_occ_mutex);
+        auto key = std::make_tuple((const void*)kern, cfg.threads, cfg.smem_bytes, cfg.cluster);
+        auto it = g_occ_cache.find(key);
+        if (it != g_occ_cache.end()) nclusters = it->second;
+        else {
+            if (cfg.cluster > 8) {
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (e != cudaSuccess) return e;
+            }
+            lc.gridDim = dim3(cfg.cluster);   // placeholder for the occupancy query
+            e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &lc);
+            if (e != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                nclusters = cfg.num_sms / cfg.cluster / 2;
+                if (nclusters < 1) nclusters = 1;
+            }
+            g_occ_cache[key] = nclusters;
+        }
+    }
     if (nclusters > cfg.needed) nclusters = cfg.needed;
     if (nclusters > cfg.max_grid) nclusters = cfg.max_grid;
     lc.gridDim = dim3((unsigned)(nclusters * cfg.cluster));
