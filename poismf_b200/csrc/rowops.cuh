@@ -13,6 +13,7 @@
 // Rows whose tile does not fit the team's shared-memory slice run the same code
 // reading the factor rows straight from global memory / L2 (tile == nullptr).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace pmf {
@@ -40,6 +41,8 @@ PMF_DEVINL void vfma(double2& acc, double c, const double2& b)
 {
     acc.x = fma(c, b.x, acc.x); acc.y = fma(c, b.y, acc.y);
 }
+template <class F> PMF_DEVINL float4 vbase(F f, int i0, float) { return make_float4(f(i0), f(i0 + 1), f(i0 + 2), f(i0 + 3)); }
+template <class F> PMF_DEVINL double2 vbase(F f, int i0, double) { return make_double2(f(i0), f(i0 + 1)); }
 PMF_DEVINL void vzero(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
 PMF_DEVINL void vzero(double2& v) { v = make_double2(0., 0.); }
 PMF_DEVINL void vaddto(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
@@ -167,19 +170,32 @@ PMF_DEVINL void dots_stream(const Team& tm, const RowView<real>& rv, const real*
     // warp's first group and predicate the memory accesses
     const int gpw = 32 / G;                                     // groups per warp
     const int sub = lane / G;
-    for (int base = (tm.rank() >> 5) * gpw; base < n; base += 2 * ngroups) {
-        const int t = base + sub, t2 = t + ngroups;
-        const bool one = t < n, two = t2 < n;
-        const VT* r0 = Fv + (size_t)rv.ind[one ? t : 0] * ldv;
-        const VT* r1 = Fv + (size_t)rv.ind[two ? t2 : 0] * ldv;
-        real s0 = 0, s1 = 0;
-        if (has0) { s0 = vdot4(a0, __ldg(r0 + c), s0); s1 = vdot4(a0, __ldg(r1 + c), s1); }
-        if (has1) { s0 = vdot4(a1, __ldg(r0 + c + 32), s0); s1 = vdot4(a1, __ldg(r1 + c + 32), s1); }
-        for (int o = G >> 1; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    constexpr int U = 4;                                        // rows in flight per lane group
+    for (int base = (tm.rank() >> 5) * gpw; base < n; base += U * ngroups) {
+        int tt[U]; bool ok[U]; const VT* r[U]; real sacc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { tt[u] = base + sub + u * ngroups; ok[u] = tt[u] < n; }
+        int id[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) id[u] = rv.ind[ok[u] ? tt[u] : 0];          // all index loads first
+#pragma unroll
+        for (int u = 0; u < U; u++) r[u] = Fv + (size_t)id[u] * ldv;
+        VT b0[U], b1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {                                           // then all row loads
+            b0[u] = has0 ? __ldg(r[u] + c) : zero;
+            b1[u] = has1 ? __ldg(r[u] + c + 32) : zero;
         }
-        if (c == 0) { if (one) out[t] = s0; if (two) out[t2] = s1; }
+#pragma unroll
+        for (int u = 0; u < U; u++) { sacc[u] = vdot4(a0, b0[u], (real)0); if (has1) sacc[u] = vdot4(a1, b1[u], sacc[u]); }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; u++) sacc[u] += __shfl_xor_sync(0xffffffffu, sacc[u], o);
+        }
+        if (c == 0) {
+#pragma unroll
+            for (int u = 0; u < U; u++) if (ok[u]) out[tt[u]] = sacc[u];
+        }
     }
     (void)gid;
 }
@@ -214,9 +230,12 @@ PMF_DEVINL void dots(const Team& tm, const RowView<real>& rv, const real* a, rea
 //           (exactly the reference's chain of axpy calls on `grad`).
 //   fast  : partial sums per thread group, then g[i] = g[i] + total.
 // `g` is a shared vector of kp reals.  Ends with a team sync.
-template <bool STRICT, class real, class Team>
-PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef, real* g)
+struct NoBase {};
+template <bool STRICT, class real, class Team, class BaseFn = NoBase>
+PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef, real* g, BaseFn basefn = BaseFn())
 {
+    // basefn(i) (fast mode only) gives the value g[i] starts from; without it g is accumulated onto
+    constexpr bool HAS_BASE = !std::is_same<BaseFn, NoBase>::value;
     const int n = rv.n;
     if (STRICT) {
         const int k = rv.k;
@@ -252,15 +271,22 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
                     p += 2 * stride;
                 }
                 if (t < n) vfma(acc0, coef[t], p[0]);
-            } else {                // tile in global memory / L2
+            } else {                // tile in global memory / L2: four independent loads in flight
                 const VT* Fv = reinterpret_cast<const VT*>(rv.F) + c;
                 const size_t ldv = (size_t)rv.ldf / V;
-                for (; t + groups < n; t += 2 * groups) {
-                    const VT b0 = __ldg(Fv + (size_t)rv.ind[t] * ldv), b1 = __ldg(Fv + (size_t)rv.ind[t + groups] * ldv);
+                VT acc2, acc3;
+                vzero(acc2); vzero(acc3);
+                for (; t + 3 * groups < n; t += 4 * groups) {
+                    const int i0 = rv.ind[t], i1 = rv.ind[t + groups], i2 = rv.ind[t + 2 * groups], i3 = rv.ind[t + 3 * groups];
+                    const VT b0 = __ldg(Fv + (size_t)i0 * ldv), b1 = __ldg(Fv + (size_t)i1 * ldv);
+                    const VT b2 = __ldg(Fv + (size_t)i2 * ldv), b3 = __ldg(Fv + (size_t)i3 * ldv);
                     vfma(acc0, coef[t], b0);
                     vfma(acc1, coef[t + groups], b1);
+                    vfma(acc2, coef[t + 2 * groups], b2);
+                    vfma(acc3, coef[t + 3 * groups], b3);
                 }
-                if (t < n) vfma(acc0, coef[t], __ldg(Fv + (size_t)rv.ind[t] * ldv));
+                for (; t < n; t += groups) vfma(acc0, coef[t], __ldg(Fv + (size_t)rv.ind[t] * ldv));
+                vaddto(acc0, acc2); vaddto(acc1, acc3);
             }
             vaddto(acc0, acc1);
         }
@@ -272,7 +298,8 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
             if (Team::is_gang) {
                 scr[rk] = tot;   // groups >= 1 here is read by nobody else: safe to overwrite slot rk
             } else {
-                VT base = gv[rk];
+                VT base;
+                if constexpr (HAS_BASE) base = vbase(basefn, rk * V, real()); else base = gv[rk];
                 vaddto(base, tot);
                 gv[rk] = base;
             }
@@ -306,10 +333,15 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
                 scr[c0] = acc0;
                 if (two) scr[c1] = acc1;
             } else {
-                VT base = gv[c0];
+                VT base;
+                if constexpr (HAS_BASE) base = vbase(basefn, c0 * V, real()); else base = gv[c0];
                 vaddto(base, acc0);
                 gv[c0] = base;
-                if (two) { VT b1 = gv[c1]; vaddto(b1, acc1); gv[c1] = b1; }
+                if (two) {
+                    VT b1;
+                    if constexpr (HAS_BASE) b1 = vbase(basefn, c1 * V, real()); else b1 = gv[c1];
+                    vaddto(b1, acc1); gv[c1] = b1;
+                }
             }
         }
     }
@@ -318,7 +350,8 @@ PMF_DEVINL void gaxpy(const Team& tm, const RowView<real>& rv, const real* coef,
         tm.sync();
         tm.nnz_vec_sum(rv.gscr, rv.ldf);
         for (int c = rk; c < L; c += sz) {
-            VT base = gv[c];
+            VT base;
+            if constexpr (HAS_BASE) base = vbase(basefn, c * V, real()); else base = gv[c];
             vaddto(base, scr[c]);
             gv[c] = base;
         }

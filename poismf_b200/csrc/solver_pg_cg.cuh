@@ -184,7 +184,11 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
     real fcur;
     {
         real ls = 0;
-        for (int t = tm.rank(); t < n; t += tm.size()) ls += xlogp(rv.xv[t], rv.pa[t]);
+        for (int t = tm.rank(); t < n; t += tm.size()) {
+            const real xt = rv.xv[t], pt = rv.pa[t];
+            ls += xlogp(xt, pt);
+            rv.pb[t] = -xt / pt;            // gradient coefficients for the first iteration
+        }
         ls = tm.nnz_sum(ls);
         real reg = 0, sq = 0;
         for (int i = kb; i < k; i += ks) { const real xi = x[i]; reg = fma(csum[i], xi, reg); sq = fma(xi, xi, sq); }
@@ -196,16 +200,16 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
     real gprev_sq = 0, fnew = 0;
 
     for (int it = 0; it < maxiter; it++) {
-        // ---- gradient at x (:231): coefficients, then one pass over the tile
-        for (int t = tm.rank(); t < n; t += tm.size()) rv.pb[t] = -rv.xv[t] / rv.pa[t];
+        // ---- gradient at x (:231): one pass over the tile.  The coefficients -x_t/p_t were
+        // refreshed when p was (f0 above / the accepted step below); w == 1 starts the
+        // accumulation from csum + 2 l2 x inside the fold (x pads are zero, so are csum's).
+        tm.sync();
         if (hc.w == (real)1) {
-            for (int i = tm.rank(); i < k; i += tm.size()) g[i] = fma(hc.two_l2, x[i], csum[i]);
+            gaxpy<false>(tm, rv, rv.pb, g, [&](int i) { return fma(hc.two_l2, x[i], csum[i]); });
         } else {
             for (int i = tm.rank(); i < k; i += tm.size()) g[i] = 0;
-        }
-        tm.sync();
-        gaxpy<false>(tm, rv, rv.pb, g);
-        if (hc.w != (real)1) {
+            tm.sync();
+            gaxpy<false>(tm, rv, rv.pb, g);
             for (int i = tm.rank(); i < k; i += tm.size()) g[i] = fma(hc.two_l2, x[i], fma(g[i], hc.w, csum[i]));
             tm.sync();
         }
@@ -303,9 +307,12 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
                 const real v = fma(step, d[i], x[i]);
                 x[i] = (v >= hc.clip_thr) ? v : (real)0;
             }
-            for (int t = tm.rank(); t < n; t += tm.size()) rv.pa[t] = fma(step, rv.pc[t], rv.pa[t]);
+            for (int t = tm.rank(); t < n; t += tm.size()) {
+                const real pt = fma(step, rv.pc[t], rv.pa[t]);
+                rv.pa[t] = pt;
+                rv.pb[t] = -rv.xv[t] / pt;
+            }
         }
-        tm.sync();
         fcur = fnew;                                               // :328 (Q4)
         gprev_sq = gg;                                             // :332
         real* tv = d; d = dprev; dprev = tv;                       // :335-339

@@ -55,6 +55,7 @@ int run_poismf(
                                (int)handle_interrupt, 0);
 }
 
+#ifndef PMF_NO_PREDICT   /* define when src/pred.c is kept whole in the wrapper build */
 /* src/pred.c:42-64.  The reference takes no dimensions (callers validate the ids,
  * poismf/__init__.py:815); the device copy needs them, so they are recovered from
  * the ids themselves: only rows up to the largest id are uploaded. */
@@ -74,6 +75,7 @@ void predict_multiple(
     if (n == 0) return;
     (void)pmf_b200_predict_multiple(PMF_DTYPE, PMF_IXB, out, A, B, ixA, ixB, n, k, dimA, dimB);
 }
+#endif
 
 /* src/topN.c:112-284 */
 int topN(
