@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: refresh replicas by peer-memory stores from the row kernels (p2p) or NCCL broadcasts")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -160,7 +162,9 @@ def main():
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     config_line = {"workload": cfg["label"], "method": cfg["method"], "k": cfg["k"], **cfg["hp"],
                    "l2_flush": "inputs larger than L2 (factors+CSR+CSC ~0.5 GB vs 126 MB)",
-                   "parallelism": f"rows/cols sharded x{args.gpus}" if args.gpus > 1 else "single GPU"}
+                   "parallelism": (f"rows/cols sharded x{args.gpus}, replicas refreshed by "
+                                   f"{'NVLink peer-memory stores fused into the row kernels' if args.exchange == 'p2p' else 'NCCL broadcasts'}")
+                   if args.gpus > 1 else "single GPU"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -201,12 +205,10 @@ def main():
         profiler = fit
     else:
         from poismf_b200.sharding import GpuBackend, ShardedSweep
-        be = GpuBackend(csr, csc, A0, B0, rank, world, local_rank)
+        be = GpuBackend(csr, csc, A0, B0, rank, world, local_rank, exchange=args.exchange)
         stream = be.stream
         drv = ShardedSweep(be, dimA, dimB, np.float32)
-        A0d, B0d = be.A.clone(), be.B.clone()
-        def reset():
-            be.A.copy_(A0d); be.B.copy_(B0d)
+        reset = lambda: be.reset(A0, B0)
         sweep = lambda: drv.run(params)
         profiler = be.fit
 
@@ -321,6 +323,36 @@ def main():
                 torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
             except Exception:
                 pass
+
+    if not args.no_e2e and world > 1:
+        # sharded public API end to end: every rank uploads ITS row/column shard and the replicated
+        # factors from host memory, runs one sharded sweep (NCCL exchange inside), reads A,B back
+        from poismf_b200.sharding import GpuBackend, ShardedSweep
+        del be
+        torch.cuda.synchronize()
+        ts = []
+        h2d = d2h = 0
+        for it in range(3):
+            dist.barrier()
+            t0 = time.perf_counter()
+            be2 = GpuBackend(csr, csc, A0, B0, rank, world, local_rank, exchange=args.exchange)
+            ShardedSweep(be2, dimA, dimB, np.float32).run(params)
+            Aout, Bout = be2.factors()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            a0, a1 = be2.rangesA[rank]; b0, b1 = be2.rangesB[rank]
+            h2d = (A0.nbytes + B0.nbytes + int(csr[1][a1] - csr[1][a0]) * 12 + int(csc[1][b1] - csc[1][b0]) * 12
+                   + (a1 - a0 + b1 - b0) * 8)
+            d2h = A0.nbytes + B0.nbytes
+            del be2
+            if it > 0:
+                ts.append(dt)
+        t = torch.tensor([float(np.mean(ts))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = 1e3 * float(t.item())
+        e2e = {"value": nnz / (e_ms / 1e3), "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e_ms, "steps": len(ts),
+               "call": "poismf_b200.sharding.GpuBackend + ShardedSweep.run(numiter=1) + factors(): per-rank shard upload, sweep with NCCL exchange, download (max over ranks)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -87,6 +87,18 @@ int pmf_b200_half_sweep(pmf_b200_handle* h, int side, const pmf_b200_params* p, 
                         double cnst_div, unsigned long long* n_unchanged);
 int pmf_b200_sync(pmf_b200_handle* h);
 
+/* ---- fused "update rows -> refresh every replica" over NVLink peer memory ----
+ * Sharded fits keep a replica of A and B on every GPU.  Instead of an NCCL collective after
+ * each half-sweep, the row kernels store every freshly solved row straight into the peers'
+ * replicas (plain stores to peer-mapped pointers; one process per GPU, so the mapping goes
+ * through CUDA IPC).  The caller only needs a stream sync + a process barrier between
+ * half-sweeps.  Usage: every rank exports its two factor buffers (64-byte handles), the
+ * handles are all-gathered by the caller (e.g. torch.distributed), every rank imports them. */
+#define PMF_B200_IPC_HANDLE_BYTES 64
+int pmf_b200_ipc_export(pmf_b200_handle* h, int which /*0=A,1=B*/, void* handle_out);
+/* handles: n_ranks x 64 bytes in rank order (own entry ignored).  n_ranks <= 8. */
+int pmf_b200_ipc_import(pmf_b200_handle* h, int which, const void* handles, int n_ranks, int self_rank);
+
 /* Per-launch device timing of the row kernels (CUDA events on the handle's stream),
  * for bench.py's roofline line: one entry per (side, row bin). */
 typedef struct pmf_b200_bin_profile {

@@ -24,7 +24,7 @@ SYMBOLS = [
     "pmf_b200_create", "pmf_b200_destroy", "pmf_b200_ldf", "pmf_b200_set_matrix",
     "pmf_b200_set_factors", "pmf_b200_get_factors", "pmf_b200_bind_factors", "pmf_b200_factor_ptr",
     "pmf_b200_set_stream", "pmf_b200_sweeps", "pmf_b200_half_sweep", "pmf_b200_sync",
-    "pmf_b200_set_profiling", "pmf_b200_get_profile",
+    "pmf_b200_set_profiling", "pmf_b200_get_profile", "pmf_b200_ipc_export", "pmf_b200_ipc_import",
     "pmf_b200_run_poismf", "pmf_b200_predict_multiple", "pmf_b200_topN", "pmf_b200_topN_batch",
 ]
 
@@ -71,6 +71,8 @@ def lib():
     L.pmf_b200_sweeps.argtypes = [vp, C.POINTER(Params)]
     L.pmf_b200_half_sweep.argtypes = [vp, i, C.POINTER(Params), d, d, C.POINTER(C.c_ulonglong)]
     L.pmf_b200_sync.argtypes = [vp]
+    L.pmf_b200_ipc_export.argtypes = [vp, i, vp]
+    L.pmf_b200_ipc_import.argtypes = [vp, i, vp, i, i]
     L.pmf_b200_set_profiling.argtypes = [vp, i]
     L.pmf_b200_get_profile.argtypes = [vp, C.POINTER(BinProfile), i]
     L.pmf_b200_run_poismf.argtypes = [i, i] + [vp] * 8 + [sz, sz, sz, d, d, d, d, i, i, sz, sz, i, i, i, i]

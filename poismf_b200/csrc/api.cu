@@ -140,6 +140,8 @@ struct pmf_b200_handle {
     virtual int half_sweep(int side, const pmf_b200_params& p, double step, double cdiv,
                            unsigned long long* n_unchanged) = 0;
     virtual int sweeps(const pmf_b200_params& p) = 0;
+    virtual int ipc_export(int which, void* out) = 0;
+    virtual int ipc_import(int which, const void* handles, int n_ranks, int self_rank) = 0;
     virtual int get_profile(pmf_b200_bin_profile* out, int max_entries) = 0;
     virtual void clear_profile() = 0;
     bool profiling = false;
@@ -160,6 +162,8 @@ template <class real> struct HandleT : pmf_b200_handle {
     unsigned long long* d_unchanged = nullptr;
     // bins of one half-sweep are independent: they are launched on a few side streams so that
     // small or latency-bound bins overlap (fork from / join to the handle's stream with events)
+    real* peer[2][7] = {};      // peers' replicas of A (0) and B (1), opened through CUDA IPC
+    int npeers[2] = {0, 0};
     static constexpr int NAUX = 6;
     cudaStream_t aux[NAUX] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
@@ -529,8 +533,12 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (S.n_empty > 0) {
             const size_t total = (size_t)S.n_empty * ldf;
             const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms * 8);
-            zero_rows_kernel<real><<<grid, 256, 0, stream>>>(M + S.row_begin * (size_t)ldf, S.d_empty, S.n_empty, ldf);
-            LAUNCHED();
+            const int wm0 = updA ? 0 : 1;
+            for (int q = -1; q < npeers[wm0]; q++) {      // own replica, then every peer's (fused exchange)
+                real* base = (q < 0 ? M : peer[wm0][q]) + S.row_begin * (size_t)ldf;
+                zero_rows_kernel<real><<<grid, 256, 0, stream>>>(base, S.d_empty, S.n_empty, ldf);
+                LAUNCHED();
+            }
         }
         CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
         if (hc.early_stop) CK(cudaMemsetAsync(d_unchanged, 0, sizeof(unsigned long long), stream));
@@ -559,6 +567,9 @@ template <class real> struct HandleT : pmf_b200_handle {
             P.gscratch = b.cap == 0 ? S.gscratch : nullptr;
             P.gs_stride = S.gs_stride;
             P.n_unchanged = d_unchanged;
+            const int wm = updA ? 0 : 1;
+            P.npeers = npeers[wm];
+            for (int q = 0; q < 7; q++) P.peerM[q] = q < npeers[wm] ? peer[wm][q] + S.row_begin * (size_t)ldf : nullptr;
             LaunchCfg cfg;
             cfg.block_team = b.block;
             cfg.cached = !strict && !(p.flags & PMF_FLAG_NO_CACHED);
@@ -599,6 +610,33 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (hc.early_stop && n_unchanged) {
             CK(cudaMemcpyAsync(n_unchanged, d_unchanged, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
+        }
+        return 0;
+    }
+
+    int ipc_export(int which, void* out) override
+    {
+        CK(cudaSetDevice(device));
+        if ((which == 0 && !ownA) || (which == 1 && !ownB))
+            return fail("ipc_export: factors are bound to caller memory; export needs handle-owned buffers");
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, which == 0 ? (void*)A : (void*)B));
+        static_assert(sizeof(hd) == PMF_B200_IPC_HANDLE_BYTES, "IPC handle size");
+        memcpy(out, &hd, sizeof hd);
+        return 0;
+    }
+    int ipc_import(int which, const void* handles, int n_ranks, int self_rank) override
+    {
+        CK(cudaSetDevice(device));
+        if (n_ranks < 1 || n_ranks > 8) return fail("ipc_import: 1..8 ranks");
+        npeers[which] = 0;
+        for (int r = 0; r < n_ranks; r++) {
+            if (r == self_rank) continue;
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char*)handles + (size_t)r * sizeof hd, sizeof hd);
+            void* ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+            peer[which][npeers[which]++] = (real*)ptr;
         }
         return 0;
     }
@@ -704,6 +742,11 @@ extern "C" int pmf_b200_half_sweep(pmf_b200_handle* h, int side, const pmf_b200_
                                    double cnst_div, unsigned long long* n_unchanged)
 {
     return h->half_sweep(side, *p, step_size, cnst_div, n_unchanged);
+}
+extern "C" int pmf_b200_ipc_export(pmf_b200_handle* h, int which, void* out) { return h->ipc_export(which, out); }
+extern "C" int pmf_b200_ipc_import(pmf_b200_handle* h, int which, const void* handles, int n_ranks, int self_rank)
+{
+    return h->ipc_import(which, handles, n_ranks, self_rank);
 }
 extern "C" int pmf_b200_set_profiling(pmf_b200_handle* h, int on)
 {

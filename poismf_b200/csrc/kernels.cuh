@@ -35,6 +35,8 @@ template <class real> struct SideParams {
     real* gscratch;        // per-CTA global scratch for rows that are not staged (3*gs_stride reals)
     long long gs_stride;
     unsigned long long* n_unchanged;  // tncg early-stop counter (src/poismf.c:393-396)
+    real* peerM[7];        // the same rows of M in the other GPUs' replicas (NVLink peer memory)
+    int npeers;            // 0: single GPU, or replicas refreshed by a collective instead
 };
 
 PMF_DEVINL int num_vecs(int method)
@@ -119,8 +121,14 @@ PMF_DEVINL void process_row(const Team& tm, const SideParams<real>& P, const Sli
         solve_tn<STRICT>(tm, rv, P.hc, V, Mrow, P.n_unchanged);
     }
     tm.sync();
-    if (tm.owns_row())
+    if (tm.owns_row()) {
         for (int i = tm.rank(); i < k; i += tm.size()) Mrow[i] = x[i];
+        // fused exchange: the solved row goes straight into every peer's replica over NVLink
+        for (int p = 0; p < P.npeers; p++) {
+            real* prow = P.peerM[p] + (size_t)row * P.ldf;
+            for (int i = tm.rank(); i < k; i += tm.size()) prow[i] = x[i];
+        }
+    }
     tm.sync();
 }
 
@@ -164,8 +172,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) rows_block_ke
 
 // One thread-block cluster per heavy row (fast numerics only: the cross-CTA fold changes
 // the summation order).  Clusters draw rows from the bin's list, longest first.
-template <class real, int METHOD, bool CACHED>
-__global__ void __launch_bounds__(512, 1) rows_cluster_kernel(const SideParams<real> P)
+// MINB = 1: resident slices (the CTA owns the SM's shared memory anyway); MINB = 2: streaming
+// slices, registers capped at 64 so that the CTA can share an SM with the short-row kernels
+template <class real, int METHOD, bool CACHED, int MINB>
+__global__ void __launch_bounds__(512, MINB) rows_cluster_kernel(const SideParams<real> P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cl = cg::this_cluster();

@@ -87,10 +87,22 @@ static cudaError_t launch_one(const LaunchCfg& cfg, const SideParams<real>& P)
 
 #if !PMF_INST_STRICT
 // ---- cluster-per-row launch (cudaLaunchKernelEx with a cluster dimension) ----
+template <class real, int METHOD, bool CACHED, int MINB>
+static cudaError_t launch_gang_thr(const LaunchCfg& cfg, const SideParams<real>& P);
+
 template <class real, int METHOD, bool CACHED>
 static cudaError_t launch_gang_one(const LaunchCfg& cfg, const SideParams<real>& P)
 {
-    auto kern = rows_cluster_kernel<real, METHOD, CACHED>;
+    // streaming (cap 0) bins are compiled for 2 CTAs per SM (64 registers) so that they can share
+    // an SM with the short-row kernels while they wait on L2
+    if (P.cap == 0) return launch_gang_thr<real, METHOD, CACHED, 2>(cfg, P);
+    return launch_gang_thr<real, METHOD, CACHED, 1>(cfg, P);
+}
+
+template <class real, int METHOD, bool CACHED, int MINB>
+static cudaError_t launch_gang_thr(const LaunchCfg& cfg, const SideParams<real>& P)
+{
+    auto kern = rows_cluster_kernel<real, METHOD, CACHED, MINB>;
     cudaError_t e = ensure_smem(kern, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t lc = {};

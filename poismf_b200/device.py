@@ -75,6 +75,15 @@ class DeviceFit:
                                             C.byref(n)))
         return n.value
 
+    def ipc_export(self, which):
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.L.pmf_b200_ipc_export(self.h, which, buf))
+        return bytes(buf)
+
+    def ipc_import(self, which, handles, self_rank):
+        blob = b"".join(handles)
+        self._ck(self.L.pmf_b200_ipc_import(self.h, which, blob, len(handles), self_rank))
+
     def set_profiling(self, on=True):
         self.L.pmf_b200_set_profiling(self.h, int(on))
 

@@ -89,28 +89,41 @@ class ShardedSweep:
 
 
 class GpuBackend:
-    """One rank's shard on one GPU: a DeviceFit bound to torch-owned replicas of A and B."""
+    """One rank's shard on one GPU.
 
-    def __init__(self, csr, csc, A0, B0, rank, world, device_index, group=None):
+    exchange="p2p"  (default): the handle owns the replicas of A and B; their CUDA IPC handles are
+        all-gathered once, and from then on the row kernels store every solved row directly into
+        all peers' replicas over NVLink (fused compute + exchange, include/poismf_b200.h).  The
+        exchange step left between half-sweeps is a stream sync + a process barrier.
+    exchange="nccl": replicas are torch tensors bound into the handle; after each half-sweep the
+        owners' rows are broadcast in place (one NCCL broadcast per owner).
+    """
+
+    def __init__(self, csr, csc, A0, B0, rank, world, device_index, group=None, exchange="p2p"):
         import torch
         import torch.distributed as dist
         from .device import DeviceFit
         from . import _lib
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = rank, world
+        self.mode = exchange if world > 1 else "local"
         dimA, k = A0.shape
         dimB = B0.shape[0]
+        self.k = k
         self.dev = torch.device("cuda", device_index)
         self.fit = DeviceFit(dimA, dimB, k, A0.dtype, device=device_index)
         ldf = self.fit.ldf
-        tdt = torch.float32 if A0.dtype == np.float32 else torch.float64
-        self.A = torch.zeros((dimA, ldf), dtype=tdt, device=self.dev)
-        self.B = torch.zeros((dimB, ldf), dtype=tdt, device=self.dev)
-        self.A[:, :k].copy_(torch.from_numpy(A0))
-        self.B[:, :k].copy_(torch.from_numpy(B0))
-        self.fit.bind_factors(self.A.data_ptr(), self.B.data_ptr())
         self.stream = torch.cuda.current_stream(self.dev)
         self.fit.set_stream(self.stream.cuda_stream)
+        if self.mode == "nccl":
+            tdt = torch.float32 if A0.dtype == np.float32 else torch.float64
+            self.A = torch.zeros((dimA, ldf), dtype=tdt, device=self.dev)
+            self.B = torch.zeros((dimB, ldf), dtype=tdt, device=self.dev)
+            self.A[:, :k].copy_(torch.from_numpy(A0))
+            self.B[:, :k].copy_(torch.from_numpy(B0))
+            self.fit.bind_factors(self.A.data_ptr(), self.B.data_ptr())
+        else:
+            self.fit.set_factors(A0, B0)
         self.rangesA = nnz_balanced_ranges(csr[1], world)
         self.rangesB = nnz_balanced_ranges(csc[1], world)
         a0, a1 = self.rangesA[rank]
@@ -120,15 +133,37 @@ class GpuBackend:
         self.local_nnz = int(lr[0].shape[0])
         self.fit.set_matrix(_lib.SIDE_CSR, *lr, row_begin=a0, n_rows=a1 - a0)
         self.fit.set_matrix(_lib.SIDE_CSC, *lc, row_begin=b0, n_rows=b1 - b0)
+        if self.mode == "p2p":
+            for which in (0, 1):
+                mine = self.fit.ipc_export(which)
+                allh = [None] * world
+                dist.all_gather_object(allh, mine, group=group)
+                self.fit.ipc_import(which, allh, rank)
         torch.cuda.synchronize(self.dev)
+        if world > 1:
+            dist.barrier(group=group)
+
+    def reset(self, A0, B0):
+        """Restore the initial factors on this rank's replica (bench warm-up)."""
+        if self.mode == "nccl":
+            self.A[:, :self.k].copy_(self.torch.from_numpy(A0))
+            self.B[:, :self.k].copy_(self.torch.from_numpy(B0))
+        else:
+            self.fit.set_factors(A0, B0)
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
 
     def half_sweep(self, side, params, step, cdiv):
         return self.fit.half_sweep(side, params, step, cdiv)
 
     def exchange(self, side):
-        """Refresh every replica with the owners' fresh rows: one broadcast per owner,
-        in place on the replicated matrix (slices are contiguous row ranges)."""
-        if self.world == 1:
+        if self.mode == "local":
+            return
+        if self.mode == "p2p":
+            # the rows already sit in every replica; wait until all ranks' stores have landed
+            self.fit.sync()
+            self.dist.barrier(group=self.group)
             return
         from . import _lib
         M, ranges = (self.A, self.rangesA) if side == _lib.SIDE_CSR else (self.B, self.rangesB)
@@ -140,5 +175,7 @@ class GpuBackend:
             w.wait()
 
     def factors(self):
-        k = self.fit.k
-        return self.A[:, :k].cpu().numpy(), self.B[:, :k].cpu().numpy()
+        if self.mode == "nccl":
+            k = self.k
+            return self.A[:, :k].cpu().numpy(), self.B[:, :k].cpu().numpy()
+        return self.fit.get_factors()

@@ -312,3 +312,56 @@ def test_lastfm_shaped_full_size_properties():
     c_funs._predict_multiple(out, A, B, ixA, ixB)
     want = np.einsum("ij,ij->i", A[ixA.astype(np.int64)].astype(np.float64), B[ixB.astype(np.int64)].astype(np.float64))
     assert np.abs(out - want).max() <= 1e-5 * max(np.abs(want).max(), 1.0)
+
+
+# ---------------------------------------------------------------- two GPUs (skipped on one)
+def _two_gpu_worker(rank, world, port, exchange, q):
+    import torch
+    import torch.distributed as dist
+    from poismf_b200 import make_params
+    from poismf_b200.sharding import GpuBackend, ShardedSweep
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    dtype = np.float32
+    csr, csc, A0, B0, k = problem("pl6k", dtype)
+    out = {}
+    for case in ("cg", "pg", "tncg"):
+        method, kw = hyper(case, k)
+        params = make_params(method, **kw)
+        be = GpuBackend(csr, csc, A0, B0, rank, world, rank, exchange=exchange)
+        ShardedSweep(be, A0.shape[0], B0.shape[0], dtype).run(params)
+        A, B = be.factors()
+        out[case] = (A.copy(), B.copy())
+        del be
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_sharded_matches_single_gpu(exchange):
+    """Sharded over 2 GPUs (replicas refreshed by peer-memory stores fused into the row kernels,
+    or by NCCL broadcasts) == the single-GPU fit, bit for bit, on every rank's replica."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, exchange, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    dtype = np.float32
+    csr, csc, A0, B0, k = problem("pl6k", dtype)
+    for case in ("cg", "pg", "tncg"):
+        method, kw = hyper(case, k)
+        A, B = A0.copy(), B0.copy()
+        assert run_device(csr, csc, A, B, method, kw) == 0
+        for r in (0, 1):
+            assert np.array_equal(res[r][case][0], A) and np.array_equal(res[r][case][1], B), (case, r)
