@@ -21,7 +21,8 @@ LIB = os.path.join(HERE, "libpoismf_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCC = os.environ.get("PMF_HOSTCC", "/usr/bin/gcc")
 
-NVFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+EXTRA = os.environ.get("PMF_NVCC_EXTRA", "").split()
+NVFLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
            "-Xcudafe", "--diag_suppress=177"]
 

@@ -206,7 +206,7 @@ template <class real> struct HandleT : pmf_b200_handle {
         CK(cudaMalloc(&csum, (size_t)kp * sizeof(real)));
         n_partial = num_sms * 4;
         CK(cudaMalloc(&partial, (size_t)n_partial * ldf * sizeof(real)));
-        CK(cudaMalloc(&counters, 64 * sizeof(int)));
+        CK(cudaMalloc(&counters, 64 * sizeof(int)));   // one per bin (<= 12 + 3 + 5)
         CK(cudaMalloc(&d_unchanged, sizeof(unsigned long long)));
         for (int i = 0; i < NAUX; i++) {
             CK(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
@@ -320,9 +320,10 @@ template <class real> struct HandleT : pmf_b200_handle {
     void* factor_ptr(int which) override { return which == 0 ? (void*)A : (void*)B; }
 
     // ---- planner: bin the local rows of one side by non-zero count -------------
+    // (sub-)warp teams need no reduction scratch: their 640 bytes go to the tile instead
     size_t slice_bytes(int team_threads, int nvec, int cap) const
     {
-        size_t b = 640 + (size_t)team_threads * 16 + (size_t)nvec * kp * sizeof(real) +
+        size_t b = (team_threads > 32 ? 640 : 0) + (size_t)team_threads * 16 + (size_t)nvec * kp * sizeof(real) +
                    (size_t)4 * cap * sizeof(real) + (size_t)cap * kp * sizeof(real);
         return round_up_sz(b, 16);
     }
@@ -337,12 +338,13 @@ template <class real> struct HandleT : pmf_b200_handle {
         // {lanes per row, tile capacity}.  Rows in flight per SM are bounded by shared memory
         // (tile + solver state per row), so capacities are graded finely; a full warp per row
         // gives the shortest per-row latency, which is what bounds throughput at that occupancy.
-        int wdef[8][2] = {{16, 16}, {32, 24}, {32, 32}, {32, 48}, {32, 64}, {32, 96}, {32, 128}, {0, 0}};
-        int nw = 7;
-        if (const char* e = getenv("POISMF_B200_WIDTHS")) {   // tuning knob: "w:cap,w:cap,..." (up to 8)
+        int wdef[12][2] = {{16, 16}, {32, 24}, {32, 32}, {32, 40}, {32, 48}, {32, 64}, {32, 80}, {32, 96},
+                           {32, 128}, {0, 0}, {0, 0}, {0, 0}};
+        int nw = 9;
+        if (const char* e = getenv("POISMF_B200_WIDTHS")) {   // tuning knob: "w:cap,w:cap,..." (up to 12)
             nw = 0;
             const char* q = e;
-            while (*q && nw < 8) {
+            while (*q && nw < 12) {
                 int w = 0, c = 0, used = 0;
                 if (sscanf(q, "%d:%d%n", &w, &c, &used) != 2) break;
                 wdef[nw][0] = w; wdef[nw][1] = c; nw++;
@@ -358,10 +360,20 @@ template <class real> struct HandleT : pmf_b200_handle {
             Bin b;
             b.block = false; b.cap = wdef[c][1]; b.width = width;
             b.slice = slice_bytes(width, nvec, b.cap);
-            int teams = 256 / width;
-            while (teams > 1 && b.slice * teams > SMEM_CTA_MAX) teams >>= 1;
-            if (b.slice * teams > SMEM_CTA_MAX) continue;
-            b.threads = std::max(teams * width, 32);
+            // teams per CTA: whatever keeps the most rows in flight per SM under the shared-memory
+            // (228 KB / SM, 1 KB reserved per CTA) and register (80 per thread) budgets
+            int best_teams = 0, best_rows = 0;
+            for (int teams = 256 / width; teams >= 1; teams >>= 1) {
+                const size_t smem = b.slice * teams;
+                if (smem > SMEM_CTA_MAX) continue;
+                const int by_smem = (int)(SMEM_PER_SM / (smem + SMEM_CTA_RESERVED));
+                const int by_regs = 65536 / (teams * width * WARP_KERNEL_REGS);
+                const int by_thr = 2048 / std::max(teams * width, 32);
+                const int ctas = std::min(std::min(by_smem, by_regs), std::min(by_thr, 32));
+                if (ctas * teams > best_rows) { best_rows = ctas * teams; best_teams = teams; }
+            }
+            if (best_teams == 0) continue;
+            b.threads = std::max(best_teams * width, 32);
             b.smem = b.slice * (b.threads / width);
             bins.push_back(b);
         }

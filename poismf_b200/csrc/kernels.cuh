@@ -18,6 +18,9 @@
 
 namespace pmf {
 
+// registers per thread the (sub-)warp kernels are compiled for (see __launch_bounds__ below)
+constexpr int WARP_KERNEL_REGS = (65536 / (256 * PMF_WARP_KERNEL_MIN_CTAS)) / 8 * 8;
+
 template <class real> struct SideParams {
     real* M;               // factors being updated  [dim   x ldf]
     const real* F;         // fixed factors          [other x ldf]
@@ -57,7 +60,7 @@ template <class real> struct Slice {
     real* tile;
     PMF_DEVINL Slice(unsigned char* base, int team_size, int nvec, int kp, int cap, bool gang = false)
     {
-        team_scratch = base; base += 640;
+        team_scratch = base; if (team_size > 32) base += 640;   // (sub-)warp teams reduce by shuffles only
         xchg = base; if (gang) base += GANG_XBYTES;
         gscr = (real*)base; base += (size_t)team_size * 16;
         vecs = (real*)base; base += (size_t)nvec * kp * sizeof(real);

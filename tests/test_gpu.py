@@ -365,3 +365,44 @@ def test_two_gpu_sharded_matches_single_gpu(exchange):
         assert run_device(csr, csc, A, B, method, kw) == 0
         for r in (0, 1):
             assert np.array_equal(res[r][case][0], A) and np.array_equal(res[r][case][1], B), (case, r)
+
+
+# ---------------------------------------------------------------- the other BASELINE shapes, scaled down
+def test_netflix_shaped_tncg_k100():
+    """BASELINE config #3 shape at 1/100 scale: few, very long columns (every column is a
+    cluster/CTA row), k=100, tncg with maxupd = 15k."""
+    from poismf_b200.synth import init_factors, powerlaw_counts
+    dtype = np.float64
+    dimA, dimB, k = 4800, 177, 100
+    csr, csc = powerlaw_counts(dimA, dimB, 250_000, alpha_a=0.5, alpha_b=0.7, dtype=dtype, seed=3)
+    A0, B0 = init_factors(dimA, dimB, k, dtype=dtype)
+    kw = dict(l2_reg=1e3, maxupd=15 * k, numiter=1)
+    Ar, Br = _oracle(dtype, csr, csc, A0, B0, "tncg", kw)
+    orc = Restatement(dtype)
+    l_ref = orc.llk(Ar, Br, csr)
+    for flags, gate in ((FLAG_STRICT, 1e-7), (0, 1e-4)):
+        A, B = A0.copy(), B0.copy()
+        assert run_device(csr, csc, A, B, "tncg", kw, flags=flags) == 0
+        assert np.isfinite(A).all() and np.isfinite(B).all() and (A >= 0).all() and (B >= 0).all()
+        l_dev = orc.llk(A, B, csr)
+        assert abs(l_dev - l_ref) <= gate * abs(l_ref), (flags, l_dev, l_ref)
+        if flags == FLAG_STRICT:
+            assert (row_rel_err(A, Ar) > 1e-9).mean() <= 0.01 and (row_rel_err(B, Br) > 1e-9).mean() <= 0.02
+
+
+def test_webscale_shaped_pg_k64():
+    """BASELINE config #4 shape at 1/500 scale: k=64, pg, maxupd=1, float32."""
+    from poismf_b200.synth import init_factors, powerlaw_counts
+    dtype = np.float32
+    dimA, dimB, k = 20_000, 2_000, 64
+    csr, csc = powerlaw_counts(dimA, dimB, 4_000_000, dtype=dtype, seed=4)
+    A0, B0 = init_factors(dimA, dimB, k, dtype=dtype)
+    kw = dict(l2_reg=1e9, step_size=1e-7, maxupd=1, numiter=3)
+    Ar, Br = _oracle(dtype, csr, csc, A0, B0, "pg", kw)
+    assert (Ar > 0).any() and (Br > 0).any()
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, "pg", kw, flags=FLAG_STRICT) == 0
+    assert np.array_equal(A, Ar) and np.array_equal(B, Br)            # heavy rows included: bit-exact
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, "pg", kw) == 0
+    assert row_rel_err(A, Ar).max() <= 1e-3 and row_rel_err(B, Br).max() <= 1e-3
