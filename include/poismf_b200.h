@@ -123,6 +123,15 @@ int pmf_b200_run_poismf(int dtype, int index_bytes,
                         int method, int limit_step, size_t numiter, size_t maxupd,
                         int early_stop, int reuse_prev, int handle_interrupt, int flags);
 
+/* Replaces factors_multiple, src/pred.c:66-199 (prototype src/poismf.h:270-280): factors for dimA
+ * NEW rows given in CSR, with B [dimB x k] and Bsum (column sums of B, l1 already added) fixed.
+ * A [dimA x k] is output only.  dimB is needed for the device copy of B (the reference takes none). */
+int pmf_b200_factors_multiple(int dtype, int index_bytes, void* A, const void* B, const void* Bsum,
+                              const void* Amean, const void* Xr, const void* Xr_indptr, const void* Xr_indices,
+                              int k, size_t dimA, size_t dimB,
+                              double l2_reg, double w_mult, double step_size, size_t niter, size_t maxupd,
+                              int method, int limit_step, int reuse_mean, int flags);
+
 /* Replaces predict_multiple, src/pred.c:42-64 (prototype src/poismf.h:250-257). */
 int pmf_b200_predict_multiple(int dtype, int index_bytes, void* out, const void* A, const void* B,
                               const void* ixA, const void* ixB, size_t n, int k,

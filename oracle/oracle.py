@@ -92,6 +92,19 @@ class Ref(_Base):
         f(_p(out), _p(A), _p(B), _p(ixA), _p(ixB), ixA.shape[0], A.shape[1], nthreads)
         return out
 
+    def factors_multiple(self, B, Bsum, Amean, csr, method, l2_reg, w_mult=1.0, step_size=1e-7, niter=10,
+                         maxupd=1, limit_step=False, reuse_mean=True, nthreads=1):
+        r = self.creal
+        Xr, ptr, ind = csr
+        dimA, k = ptr.shape[0] - 1, B.shape[1]
+        A = np.empty((dimA, k), dtype=self.dtype)
+        f = self.lib.factors_multiple
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 7 + [C.c_int, _sz, r, r, r, _sz, _sz, C.c_int, C.c_bool, C.c_bool, C.c_int]
+        rc = f(_p(A), _p(B), _p(Bsum), _p(Amean), _p(Xr), _p(ptr), _p(ind), k, dimA, l2_reg, w_mult, step_size,
+               niter, maxupd, METHODS[method], limit_step, reuse_mean, nthreads)
+        return rc, A
+
     def topN(self, a_vec, B, n_top, include=None, exclude=None, nthreads=1):
         out_ix = np.empty(n_top, dtype=np.uint64)
         out_sc = np.empty(n_top, dtype=self.dtype)
@@ -127,6 +140,19 @@ class Restatement(_Base):
         return f(_p(A), _p(Xr), _p(Xr_ptr), _p(Xr_ind), _p(B), _p(Xc), _p(Xc_ptr), _p(Xc_ind),
                  A.shape[0], B.shape[0], A.shape[1], l2_reg, l1_reg, w_mult, step_size,
                  METHODS[method], int(limit_step), numiter, maxupd, int(early_stop), int(reuse_prev))
+
+    def factors_multiple(self, B, Bsum, Amean, csr, method, l2_reg, w_mult=1.0, step_size=1e-7, niter=10,
+                         maxupd=1, limit_step=False, reuse_mean=True):
+        r = self.creal
+        Xr, ptr, ind = csr
+        dimA, k = ptr.shape[0] - 1, B.shape[1]
+        A = np.empty((dimA, k), dtype=self.dtype)
+        f = self.lib.oracle_factors_multiple
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 7 + [C.c_int, _sz, r, r, r, _sz, _sz, C.c_int, C.c_int, C.c_int]
+        rc = f(_p(A), _p(B), _p(Bsum), _p(Amean), _p(Xr), _p(ptr), _p(ind), k, dimA, l2_reg, w_mult, step_size,
+               niter, maxupd, METHODS[method], int(limit_step), int(reuse_mean))
+        return rc, A
 
     def eval(self, a, F, csum, xval, xind, l2, w):
         """(f_cg, g_cg, f_tn, g_tn) at point a for one row."""

@@ -1067,6 +1067,53 @@ int oracle_half_sweep(int method, real *M, const real *F, const real *xv, const 
     return 0;
 }
 
+
+/* src/pred.c:66-199  factors_multiple: factors for new rows, B and Bsum (already +l1) fixed.
+ * pg: niter proximal steps with halving step size, Bsum scaled by -step ONCE per iteration
+ * (w==1), while for w!=1 the weighted sums are scaled by -step0 at :126 and AGAIN by the current
+ * -step at :160 (kept as is); cg: one solve with maxupd*niter iterations; tncg: one solve,
+ * starting from Amean iff reuse_mean. */
+int oracle_factors_multiple(real *A, const real *B, const real *Bsum, const real *Amean,
+                            const real *Xr, const ix_t *Xr_indptr, const ix_t *Xr_indices,
+                            int k_int, size_t dimA, real l2_reg, real w_mult, real step_size,
+                            size_t niter, size_t maxupd, int method, int limit_step, int reuse_mean)
+{
+    size_t k = (size_t)k_int;
+    real *buf = (real *)malloc(sizeof(real) * 22 * k);
+    int *ibuf = (int *)malloc(sizeof(int) * k);
+    real *scaled = (real *)malloc(sizeof(real) * k);
+    real *csum_w = NULL, *csum_w_scaled = NULL;
+    if (w_mult != 1.) {
+        csum_w = (real *)malloc(sizeof(real) * k * dimA);
+        weighted_sums(B, Bsum, csum_w, Xr_indices, Xr_indptr, dimA, k, w_mult);
+        if (method == 3) {
+            for (size_t i = 0; i < dimA * k; i++) csum_w[i] *= -step_size;           /* :126 */
+            csum_w_scaled = (real *)malloc(sizeof(real) * k * dimA);
+        }
+    }
+    if (reuse_mean || method != 1)                                                  /* :144-147 */
+        for (size_t r = 0; r < dimA; r++) memcpy(A + r * k, Amean, k * sizeof(real));
+    if (method == 3) {
+        for (size_t it = 0; it < niter; it++) {                                     /* :152-167 */
+            if (w_mult == 1.) { memcpy(scaled, Bsum, sizeof(real) * k); vscal(k_int, -step_size, scaled); }
+            else { memcpy(csum_w_scaled, csum_w, sizeof(real) * k * dimA);
+                   for (size_t i = 0; i < dimA * k; i++) csum_w_scaled[i] *= -step_size; }
+            real cdiv = 1. / (1. + 2. * l2_reg * step_size);
+            half_sweep(3, A, B, Xr, Xr_indptr, Xr_indices, dimA, k, scaled, csum_w_scaled, l2_reg, w_mult,
+                       step_size, cdiv, maxupd, 0, 0, 0, buf, ibuf);
+            step_size *= 0.5;
+        }
+    } else if (method == 2) {                                                       /* :171-178 */
+        half_sweep(2, A, B, Xr, Xr_indptr, Xr_indices, dimA, k, Bsum, csum_w, l2_reg, w_mult,
+                   step_size, 0, maxupd * niter, limit_step, 0, 0, buf, ibuf);
+    } else {                                                                        /* :180-188 */
+        half_sweep(1, A, B, Xr, Xr_indptr, Xr_indices, dimA, k, Bsum, csum_w, l2_reg, w_mult,
+                   step_size, 0, maxupd, 0, reuse_mean, 0, buf, ibuf);
+    }
+    free(buf); free(ibuf); free(scaled); free(csum_w); free(csum_w_scaled);
+    return 0;
+}
+
 /* Single-row entry points for known-answer tests (cg / tncg solvers alone). */
 void oracle_cg_row(real *a, const real *F, const real *csum, const real *xval,
                    const ix_t *xind, ix_t nnz, int k, real l2, real w,

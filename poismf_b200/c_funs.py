@@ -50,6 +50,24 @@ def _run_poismf(Xr, Xr_indices, Xr_indptr, Xc, Xc_indices, Xc_indptr, A, B,
     return rc
 
 
+def _predict_factors_multiple(B, Bsum, Amean, Xr_indptr, Xr_indices, Xr, l2_reg=1e9, w_mult=1.0, step_size=1e-7,
+                              niter=10, maxupd=1, method="tncg", limit_step=False, reuse_mean=True, nthreads=1,
+                              flags=0):
+    """poismf_c_wrapper.pxi:147-206 — factors for new rows (PoisMF.transform / predict_factors)."""
+    _lib.require_gpu()
+    k = B.shape[1]
+    dimA = Xr_indptr.shape[0] - 1
+    A = np.empty((dimA, k), dtype=B.dtype)
+    rc = _lib.lib().pmf_b200_factors_multiple(
+        _lib.dtype_code(B.dtype), _lib.index_bytes(Xr_indptr), _lib.ptr(A), _lib.ptr(B), _lib.ptr(Bsum),
+        _lib.ptr(Amean), _lib.ptr(Xr), _lib.ptr(Xr_indptr), _lib.ptr(Xr_indices), k, dimA, B.shape[0],
+        float(l2_reg), float(w_mult), float(step_size), int(niter), int(maxupd), _lib.METHODS[method],
+        int(bool(limit_step)), int(bool(reuse_mean)), int(flags))
+    if rc:
+        raise MemoryError("Could not allocate enough memory.")
+    return A
+
+
 def _predict_multiple(out, A, B, ix_u, ix_i, nthreads=1):
     _lib.require_gpu()
     rc = _lib.lib().pmf_b200_predict_multiple(

@@ -140,6 +140,8 @@ struct pmf_b200_handle {
     virtual int half_sweep(int side, const pmf_b200_params& p, double step, double cdiv,
                            unsigned long long* n_unchanged) = 0;
     virtual int sweeps(const pmf_b200_params& p) = 0;
+    virtual int factors_multiple(void* A_out, const void* Bsum, const void* Amean, const pmf_b200_params& p,
+                                 int reuse_mean) = 0;
     virtual int ipc_export(int which, void* out) = 0;
     virtual int ipc_import(int which, const void* handles, int n_ranks, int self_rank) = 0;
     virtual int get_profile(pmf_b200_bin_profile* out, int max_entries) = 0;
@@ -507,6 +509,14 @@ template <class real> struct HandleT : pmf_b200_handle {
     int half_sweep(int side, const pmf_b200_params& p, double step_d, double cdiv_d,
                    unsigned long long* n_unchanged) override
     {
+        return half_sweep_ex(side, p, step_d, cdiv_d, n_unchanged, nullptr, (real)1, -1);
+    }
+    // csum_host != nullptr: use these k column sums (already +l1 and, for pg, pre-scaled) instead of
+    // summing the fixed matrix; maxupd_override >= 0 replaces p.maxupd (factors_multiple's cg)
+    int half_sweep_ex(int side, const pmf_b200_params& p, double step_d, double cdiv_d,
+                      unsigned long long* n_unchanged, const real* csum_host, real pre_scale,
+                      long long maxupd_override)
+    {
         CK(cudaSetDevice(device));
         Side<real>& S = sides[side];
         if (!S.ptr) return fail("half_sweep: matrix for side %d not set", side);
@@ -532,7 +542,8 @@ template <class real> struct HandleT : pmf_b200_handle {
             if ((double)c < 1e-15) c = std::nextafter(c, (real)1);
             hc.clip_thr = c;
         }
-        hc.maxupd = (int)std::min<size_t>(p.maxupd, (size_t)INT32_MAX);
+        hc.maxupd = (int)std::min<size_t>(maxupd_override >= 0 ? (size_t)maxupd_override : p.maxupd, (size_t)INT32_MAX);
+        hc.pre_scale = pre_scale;
         hc.limit_step = p.limit_step; hc.reuse_prev = p.reuse_prev;
         hc.early_stop = (p.method == PMF_TNCG && p.early_stop) ? 1 : 0;
         hc.method = p.method;
@@ -540,7 +551,8 @@ template <class real> struct HandleT : pmf_b200_handle {
         ColsumFinal<real> fin;
         fin.l1 = l1; fin.scale1 = -step; fin.scale2 = -step; fin.nscale = 0;
         if (p.method == PMF_PG && w == (real)1) fin.nscale = updA ? 2 : 1;   // Q1: A side scaled twice
-        if (column_sums(F, other, fin, strict)) return 1;
+        if (csum_host) CK(cudaMemcpyAsync(csum, csum_host, (size_t)k * sizeof(real), cudaMemcpyHostToDevice, stream));
+        else if (column_sums(F, other, fin, strict)) return 1;
 
         if (S.n_empty > 0) {
             const size_t total = (size_t)S.n_empty * ldf;
@@ -678,6 +690,48 @@ template <class real> struct HandleT : pmf_b200_handle {
                 }
             }
         return n;
+    }
+
+    // ---- factors_multiple (src/pred.c:66-199): rows of A for new data, B and Bsum fixed ---------
+    // The handle holds the new rows' CSR on the CSR side and B; A (dimA rows) is produced here.
+    int factors_multiple(void* A_out, const void* Bsum_v, const void* Amean_v, const pmf_b200_params& p,
+                         int reuse_mean) override
+    {
+        CK(cudaSetDevice(device));
+        const real* Bsum = (const real*)Bsum_v;
+        const real* Amean = (const real*)Amean_v;
+        const real l2 = (real)p.l2_reg, w = (real)p.w_mult;
+        real step = (real)p.step_size;
+        {   // initialise every row to the mean of the old A (:144-147); tncg without reuse_mean starts
+            // from 1e-3 inside the solver, rows are zero-filled here only to be deterministic
+            std::vector<real> init(dimA * (size_t)k, (real)0);
+            if (reuse_mean || p.method != PMF_TNCG)
+                for (size_t r = 0; r < dimA; r++) memcpy(&init[r * k], Amean, (size_t)k * sizeof(real));
+            if (copy_in(A, init.data(), dimA)) return 1;
+            CK(cudaStreamSynchronize(stream));
+        }
+        pmf_b200_params q = p;
+        q.early_stop = 0;
+        std::vector<real> scaled(k);
+        if (p.method == PMF_PG) {
+            const real step0 = step;
+            for (size_t it = 0; it < p.numiter; it++) {                               // :152-167
+                for (int c = 0; c < k; c++) scaled[c] = Bsum[c] * (-step);            // w == 1: scaled once
+                const real* cs = (w == (real)1) ? scaled.data() : Bsum;               // w != 1: raw sums, scaled in-kernel
+                const double cdiv = (double)(real)(1. / (1. + 2. * (double)l2 * (double)step));
+                if (half_sweep_ex(PMF_SIDE_CSR, q, (double)step, cdiv, nullptr, cs, -step0, -1)) return 1;
+                CK(cudaStreamSynchronize(stream));   // `scaled` is re-used by the next iteration
+                step = (real)((double)step * 0.5);
+            }
+        } else if (p.method == PMF_CG) {                                              // :171-178
+            if (half_sweep_ex(PMF_SIDE_CSR, q, (double)step, 1.0, nullptr, Bsum, (real)1,
+                              (long long)(p.maxupd * p.numiter))) return 1;
+        } else {                                                                      // :180-188
+            q.reuse_prev = reuse_mean;
+            if (half_sweep_ex(PMF_SIDE_CSR, q, (double)step, 1.0, nullptr, Bsum, (real)1, -1)) return 1;
+        }
+        CK(cudaStreamSynchronize(stream));
+        return get_factors(A_out, nullptr);
     }
 
     // ---- numiter alternating sweeps (src/poismf.c:506-608) -------------------------
@@ -858,6 +912,31 @@ extern "C" int pmf_b200_run_poismf(int dtype, int index_bytes,
         if (was_interrupted && !handle_interrupt) raise(SIGINT);
     }
     return rc;
+}
+
+// ---- factors_multiple drop-in (src/pred.c:66-199, prototype src/poismf.h:270-280) ------------
+extern "C" int pmf_b200_factors_multiple(int dtype, int index_bytes, void* A, const void* B, const void* Bsum,
+                                         const void* Amean, const void* Xr, const void* Xr_indptr,
+                                         const void* Xr_indices, int k, size_t dimA, size_t dimB,
+                                         double l2_reg, double w_mult, double step_size, size_t niter, size_t maxupd,
+                                         int method, int limit_step, int reuse_mean, int flags)
+{
+    pmf_b200_handle* h = pmf_b200_create(dtype, dimA, dimB, (size_t)k, env_device());
+    if (!h) return 1;
+    const size_t nnz = index_bytes == 8 ? (size_t)((const uint64_t*)Xr_indptr)[dimA] - (size_t)((const uint64_t*)Xr_indptr)[0]
+                                        : (size_t)(((const int*)Xr_indptr)[dimA] - ((const int*)Xr_indptr)[0]);
+    int rc = h->set_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, nnz, index_bytes, 0, dimA);
+    if (!rc) rc = h->set_factors(nullptr, B);
+    if (!rc) {
+        pmf_b200_params p;
+        p.l2_reg = l2_reg; p.l1_reg = 0; p.w_mult = w_mult; p.step_size = step_size; p.method = method;
+        p.limit_step = limit_step; p.numiter = niter; p.maxupd = maxupd; p.early_stop = 0; p.reuse_prev = 0;
+        p.flags = env_flags(flags);
+        rc = h->factors_multiple(A, Bsum, Amean, p, reuse_mean);
+    }
+    pmf_b200_destroy(h);
+    if (rc) fprintf(stderr, "Error: out of memory.\n");
+    return rc ? 1 : 0;
 }
 
 // ---- predict_multiple drop-in ------------------------------------------------

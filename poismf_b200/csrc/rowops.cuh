@@ -385,6 +385,8 @@ template <class real> struct HalfSweepConsts {
     real wm1;       // (real)(w_mult - 1.)  src/poismf.c:113
     real step_w;    // pg: step_size * w_mult      (:151)
     real neg_step;  // pg: -step_size              (:460,:533)
+    real pre_scale; // pg, w != 1: extra factor on the weighted sums (1 in run_poismf; -step0 in
+                    // factors_multiple, which scales them twice: src/pred.c:126 and :160)
     real cdiv;      // pg: 1/(1+2*l2*step)         (:511)
     real clip_thr;  // smallest `real` v with (double)v >= 1e-15: the cg clip of nonnegcg.c:303 in `real` arithmetic
     int maxupd;
@@ -406,7 +408,7 @@ PMF_DEVINL void weighted_colsum(const Team& tm, const RowView<real>& rv, const r
     for (int i = tm.rank(); i < k; i += tm.size()) {
         real v = mul<STRICT>(out[i], hc.wm1);
         v = add<STRICT>(v, csum[i]);
-        if (hc.method == M_PG) v = mul<STRICT>(v, hc.neg_step);
+        if (hc.method == M_PG) { v = mul<STRICT>(v, hc.pre_scale); v = mul<STRICT>(v, hc.neg_step); }
         out[i] = v;
     }
     tm.sync();

@@ -77,6 +77,31 @@ void predict_multiple(
 }
 #endif
 
+#ifndef PMF_NO_FACTORS   /* define when src/pred.c is kept whole in the wrapper build */
+/* src/pred.c:66-199.  B's row count is not an argument of the reference: it is recovered from the
+ * largest item id among the new rows (rows of B beyond it are never read). */
+int factors_multiple(
+    real_t *A, real_t *B,
+    real_t *Bsum, real_t *Amean,
+    real_t *Xr, sparse_ix *Xr_indptr, sparse_ix *Xr_indices,
+    int k, size_t dimA,
+    real_t l2_reg, real_t w_mult,
+    real_t step_size, size_t niter, size_t maxupd,
+    Method method, bool limit_step, bool reuse_mean,
+    int nthreads)
+{
+    (void)nthreads;
+    size_t dimB = 0;
+    const size_t nnz = (size_t)Xr_indptr[dimA] - (size_t)Xr_indptr[0];
+    for (size_t i = 0; i < nnz; i++)
+        if ((size_t)Xr_indices[i] + 1 > dimB) dimB = (size_t)Xr_indices[i] + 1;
+    if (dimB == 0) dimB = 1;
+    return pmf_b200_factors_multiple(PMF_DTYPE, PMF_IXB, A, B, Bsum, Amean, Xr, Xr_indptr, Xr_indices, k, dimA, dimB,
+                                     (double)l2_reg, (double)w_mult, (double)step_size, niter, maxupd,
+                                     (int)method, (int)limit_step, (int)reuse_mean, 0);
+}
+#endif
+
 /* src/topN.c:112-284 */
 int topN(
     real_t *restrict a_vec, real_t *restrict B, int k,

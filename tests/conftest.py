@@ -88,3 +88,31 @@ def run_device(csr, csc, A, B, method, kw, flags=0):
 
 def row_rel_err(X, Y):
     return np.linalg.norm(X - Y, axis=1) / np.maximum(np.linalg.norm(Y, axis=1), 1e-30)
+
+
+FM_CASES = {
+    "pg": ("pg", dict(l2_reg=1e3, step_size=1e-4, niter=4, maxupd=2)),
+    "pg_w": ("pg", dict(l2_reg=1e3, step_size=1e-4, niter=3, maxupd=1, w_mult=2.0)),
+    "cg": ("cg", dict(l2_reg=1e3, niter=3, maxupd=2, limit_step=True)),
+    "cg_w": ("cg", dict(l2_reg=1e3, niter=2, maxupd=3, w_mult=1.5)),
+    "tncg": ("tncg", dict(l2_reg=1e3, maxupd=None)),
+    "tncg_w_nomean": ("tncg", dict(l2_reg=1e3, maxupd=None, reuse_mean=False, w_mult=2.0)),
+}
+
+
+def fm_problem(name, dtype):
+    """Inputs of factors_multiple: new rows = the problem's CSR, B random non-negative, Bsum = colsum + l1."""
+    csr, csc, A0, B0, k = problem(name, dtype)
+    rng = np.random.default_rng(5)
+    B = np.ascontiguousarray(rng.gamma(1, 0.3, size=B0.shape).astype(dtype))
+    Bsum = np.ascontiguousarray((B.sum(0) + 0.1).astype(dtype))
+    Amean = np.ascontiguousarray(rng.gamma(1, .3, size=k).astype(dtype))
+    return csr, B, Bsum, Amean, k
+
+
+def fm_hyper(case, k):
+    method, kw = FM_CASES[case]
+    kw = dict(kw)
+    if kw.get("maxupd", 0) is None:
+        kw["maxupd"] = 15 * k
+    return method, kw

@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
-from conftest import CASES, hyper, problem  # noqa: E402
+from conftest import CASES, FM_CASES, fm_hyper, fm_problem, hyper, problem  # noqa: E402
 from oracle.oracle import Ref  # noqa: E402
 
 
@@ -33,6 +33,13 @@ def main():
                 assert rc == 0
                 out[f"{prob}/{np.dtype(dt).name}/{case}/A"] = A
                 out[f"{prob}/{np.dtype(dt).name}/{case}/B"] = B
+        # factors_multiple (src/pred.c:66-199) on the README shape
+        csr, B, Bsum, Amean, k = fm_problem("readme", dt)
+        for case in FM_CASES:
+            method, kw = fm_hyper(case, k)
+            rc, A = ref.factors_multiple(B, Bsum, Amean, csr, method, **kw)
+            assert rc == 0
+            out[f"factors_multiple/{np.dtype(dt).name}/{case}"] = A
         # predict_multiple and topN known answers on the README factors
         csr, csc, A0, B0, k = problem("readme", dt)
         rng = np.random.default_rng(3)

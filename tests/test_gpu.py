@@ -17,7 +17,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import CASES, ROOT, hyper, problem, row_rel_err, run_device
+from conftest import CASES, FM_CASES, ROOT, fm_hyper, fm_problem, hyper, problem, row_rel_err, run_device
 from oracle.oracle import Restatement
 
 pytestmark = pytest.mark.gpu
@@ -406,3 +406,26 @@ def test_webscale_shaped_pg_k64():
     A, B = A0.copy(), B0.copy()
     assert run_device(csr, csc, A, B, "pg", kw) == 0
     assert row_rel_err(A, Ar).max() <= 1e-3 and row_rel_err(B, Br).max() <= 1e-3
+
+
+# ---------------------------------------------------------------- factors_multiple
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", list(FM_CASES))
+def test_factors_multiple_matches_oracle(dtype, case):
+    from poismf_b200 import c_funs
+    for prob in ("readme", "pl2k"):
+        csr, B, Bsum, Amean, k = fm_problem(prob, dtype)
+        method, kw = fm_hyper(case, k)
+        rc, Ar = Restatement(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
+        assert rc == 0
+        A = c_funs._predict_factors_multiple(B, Bsum, Amean, csr[1], csr[2], csr[0], method=method,
+                                             flags=FLAG_STRICT, **kw)
+        if method == "pg":
+            assert np.array_equal(A, Ar)
+        else:
+            tol = 1e-9 if dtype == np.float64 else 1e-5
+            assert (row_rel_err(A, Ar) > tol).mean() <= 0.005
+        if method == "pg" or (method == "cg" and dtype == np.float64 and kw.get("limit_step")):
+            A = c_funs._predict_factors_multiple(B, Bsum, Amean, csr[1], csr[2], csr[0], method=method, **kw)
+            gate = 1e-5 if dtype == np.float64 else 1e-3
+            assert (row_rel_err(A, Ar) > gate).mean() <= 0.002

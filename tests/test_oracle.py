@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import CASES, hyper, problem
+from conftest import CASES, FM_CASES, fm_hyper, fm_problem, hyper, problem
 from oracle.oracle import Ref, Restatement
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
@@ -73,3 +73,21 @@ def test_llk_matches_numpy():
     pred = np.einsum("ij,ij->i", A0[rows], B0[csr[2].astype(np.int64)])
     want = (csr[0] * np.log(pred)).sum() - A0.sum(0) @ B0.sum(0)
     assert abs(orc.llk(A0, B0, csr) - want) <= 1e-9 * abs(want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", list(FM_CASES))
+def test_factors_multiple_restatement(dtype, case):
+    """factors_multiple (src/pred.c:66-199): restatement == committed reference outputs (README shape)
+    and == the reference build on a power-law shape when oracle/_ref is present."""
+    name = np.dtype(dtype).name
+    csr, B, Bsum, Amean, k = fm_problem("readme", dtype)
+    method, kw = fm_hyper(case, k)
+    rc, A = Restatement(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
+    assert rc == 0 and np.array_equal(A, GOLD[f"factors_multiple/{name}/{case}"])
+    if Ref.available(dtype):
+        csr, B, Bsum, Amean, k = fm_problem("pl2k", dtype)
+        method, kw = fm_hyper(case, k)
+        rc1, A1 = Ref(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
+        rc2, A2 = Restatement(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
+        assert rc1 == 0 and rc2 == 0 and np.array_equal(A1, A2)
