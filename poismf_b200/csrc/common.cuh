@@ -83,8 +83,10 @@ template <bool STRICT> PMF_DEVINL double xlogp_acc(double acc, double x, double 
     if (STRICT) return __dadd_rn(acc, __dmul_rn(x, log(p)));
     return fma(x, log(p), acc);
 }
-// The per-nnz term alone (for two-level summation in fast mode)
-PMF_DEVINL float xlogp(float x, float p) { return x * logf(p); }
+// The per-nnz term alone (for two-level summation in fast mode).  Float uses the hardware
+// log2 (MUFU.LG2, |abs err| < 4e-7 on [0.5,2], <= 2 ulp elsewhere): the term feeds only the
+// line-search comparisons of the fast path, whose float noise floor is far above that.
+PMF_DEVINL float xlogp(float x, float p) { return x * __logf(p); }
 PMF_DEVINL double xlogp(double x, double p) { return x * log(p); }
 
 PMF_DEVINL bool is_bad(float v) { return isnan(v) || isinf(v); }

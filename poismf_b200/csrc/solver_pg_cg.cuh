@@ -181,7 +181,7 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
     const int maxiter = hc.maxupd <= 0 ? INT32_MAX : hc.maxupd;
 
     dots<false>(tm, rv, x, rv.pa);                                // p_t = <x, F_t>
-    real fcur;
+    real fcur, regx;          // regx = <csum,x> + l2 |x|^2 at the current x, carried across iterations
     {
         real ls = 0;
         for (int t = tm.rank(); t < n; t += tm.size()) {
@@ -193,7 +193,8 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
         real reg = 0, sq = 0;
         for (int i = kb; i < k; i += ks) { const real xi = x[i]; reg = fma(csum[i], xi, reg); sq = fma(xi, xi, sq); }
         reg = tm.ksum(reg); sq = tm.ksum(sq);
-        fcur = fma(hc.l2, sq, reg) - ls * hc.w;                   // nonnegcg.c:191
+        regx = fma(hc.l2, sq, reg);
+        fcur = regx - ls * hc.w;                                  // nonnegcg.c:191
     }
     if (is_bad(fcur)) return;
     int nfe = 1;
@@ -215,11 +216,11 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
         }
         // ---- direction (:236-261) and every k-scalar of this iteration.  Executed by the k
         // leader (the whole (sub-)warp team, or warp 0 of a CTA team, which then broadcasts).
-        // Besides <g,d>, |d|^2, |g|^2 and the step bound it collects the dot products from which
-        // the regulariser of every trial point follows in O(1):
-        //   <csum, x+s d> = cx + s cd,   |x+s d|^2 = xx + 2 s xd + s^2 dd
-        // (the clip at 1e-15 moves these by < 1e-15 |csum|: inside the cached search's tolerance)
-        real gd = 0, dsq = 0, gg = 0, smax = (real)1, cx = 0, cd = 0, xx = 0, xd = 0;
+        // Besides <g,d>, |d|^2, |g|^2 and the step bound it collects lin = <csum + 2 l2 x, d>, from
+        // which the regulariser of every trial point follows in O(1):
+        //   <csum,x+s d> + l2 |x+s d|^2 = regx + s lin + s^2 l2 |d|^2
+        // (the clip at 1e-15 moves this by < 1e-15 |csum|: inside the cached search's tolerance)
+        real gd = 0, dsq = 0, gg = 0, smax = (real)1, lin = 0;
         if (tm.k_leader()) {
             real theta = 0, beta = 0;
             if (it > 0) {
@@ -239,21 +240,21 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
                 if (it > 0 && !(xi <= (real)0)) di += beta * dprev[i] - theta * (gi - gprev[i]);
                 d[i] = di;
                 gd = fma(gi, di, gd); dsq = fma(di, di, dsq); gg = fma(gi, gi, gg);
-                cx = fma(ci, xi, cx); cd = fma(ci, di, cd); xx = fma(xi, xi, xx); xd = fma(xi, di, xd);
+                lin = fma(fma(hc.two_l2, xi, ci), di, lin);
                 if (di < (real)0) { const real r = -xi / di; m = (r < m) ? r : m; }  // limit_step (:272-279)
             }
             gd = tm.ksum(gd); dsq = tm.ksum(dsq); gg = tm.ksum(gg);
-            cx = tm.ksum(cx); cd = tm.ksum(cd); xx = tm.ksum(xx); xd = tm.ksum(xd);
+            lin = tm.ksum(lin);
             smax = tm.kmin(m);
             if (Team::k_bcast && kb == 0) {
                 real* ksl = tm.template kslots<real>();
-                ksl[0] = gd; ksl[1] = dsq; ksl[2] = gg; ksl[3] = cx; ksl[4] = cd; ksl[5] = xx; ksl[6] = xd; ksl[7] = smax;
+                ksl[0] = gd; ksl[1] = dsq; ksl[2] = gg; ksl[3] = lin; ksl[4] = smax;
             }
         }
         tm.sync();                                                 // d (and the scalars) visible to everyone
         if (Team::k_bcast) {
             const real* ksl = tm.template kslots<real>();
-            gd = ksl[0]; dsq = ksl[1]; gg = ksl[2]; cx = ksl[3]; cd = ksl[4]; xx = ksl[5]; xd = ksl[6]; smax = ksl[7];
+            gd = ksl[0]; dsq = ksl[1]; gg = ksl[2]; lin = ksl[3]; smax = ksl[4];
         }
         if (fabs((double)gd) <= (double)tol) return;               // :264-269
 
@@ -262,8 +263,9 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
         // ---- line search (:297-327): first trial alone, then four at a time
         real step = smax;
         bool accepted = false;
+        const real l2dd = hc.l2 * dsq;
         auto freg = [&](real sj) {   // <csum,x'> + l2 |x'|^2 at x' = x + sj d
-            return fma(hc.l2, fma(sj, fma(sj, dsq, xd + xd), xx), fma(sj, cd, cx));
+            return fma(sj, fma(sj, l2dd, lin), regx);
         };
         {
             real lsum = 0;
@@ -303,6 +305,7 @@ PMF_DEVINL void solve_cg_cached(const Team& tm, const RowView<real>& rv, const H
             if (!accepted) { step = steps[nb - 1]; ls += nb; }
         }
         if (accepted) {
+            regx = freg(step);
             for (int i = tm.rank(); i < k; i += tm.size()) {
                 const real v = fma(step, d[i], x[i]);
                 x[i] = (v >= hc.clip_thr) ? v : (real)0;
