@@ -340,8 +340,11 @@ template <class real> struct HandleT : pmf_b200_handle {
         // {lanes per row, tile capacity}.  Rows in flight per SM are bounded by shared memory
         // (tile + solver state per row), so capacities are graded finely; a full warp per row
         // gives the shortest per-row latency, which is what bounds throughput at that occupancy.
-        int wdef[12][2] = {{16, 16}, {32, 24}, {32, 32}, {32, 40}, {32, 48}, {32, 64}, {32, 80}, {32, 96},
-                           {32, 128}, {0, 0}, {0, 0}, {0, 0}};
+        // (64 = a two-warp CTA per row: from ~64 non-zeros on, shared memory leaves fewer than 16 rows
+        // in flight per SM and one warp per row no longer hides the latencies; measured on B200)
+        int wdef[12][2] = {{16, 16}, {32, 24}, {32, 32}, {32, 40}, {32, 48}, {64, 64}, {64, 80}, {64, 96},
+                           {64, 128}, {0, 0}, {0, 0}, {0, 0}};
+        if (strict) for (int c = 5; c < 9; c++) wdef[c][0] = 32;   // strict: warp and 256-thread CTA teams only
         int nw = 9;
         if (const char* e = getenv("POISMF_B200_WIDTHS")) {   // tuning knob: "w:cap,w:cap,..." (up to 12)
             nw = 0;
@@ -356,9 +359,19 @@ template <class real> struct HandleT : pmf_b200_handle {
         }
         for (int c = 0; c < nw; c++) {
             const int width = wdef[c][0];
-            if (width != 8 && width != 16 && width != 32) continue;
             if (c > 0 && wdef[c][1] <= wdef[c - 1][1]) continue;
-            if (strict && width < 32) continue;
+            if (width == 64 || width == 128) {
+                // a small CTA (2 or 4 warps) per row: for capacities where shared memory leaves so few
+                // rows in flight per SM that one warp per row cannot hide latency
+                Bin b;
+                b.block = true; b.cap = wdef[c][1]; b.threads = width;
+                b.slice = slice_bytes(width, nvec, b.cap);
+                b.smem = b.slice;
+                if (b.smem > SMEM_CTA_MAX) continue;
+                bins.push_back(b);
+                continue;
+            }
+            if (width != 8 && width != 16 && width != 32) continue;
             Bin b;
             b.block = false; b.cap = wdef[c][1]; b.width = width;
             b.slice = slice_bytes(width, nvec, b.cap);
