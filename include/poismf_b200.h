@@ -152,6 +152,11 @@ int pmf_b200_topN_batch(int dtype, int index_bytes, const void* A, const void* B
                         const void* excl_ptr, const void* excl_ix,
                         void* outp_ix, void* outp_score, size_t n_top, size_t n);
 
+/* Counters of the calling thread's topN calls: users scored by the tensor-core candidate scorer,
+ * and how many of those had to be redone by the exact scorer because the TF32 error bound could
+ * not prove their candidate set complete. */
+void pmf_b200_topN_stats(unsigned long long* tensor_core_users, unsigned long long* redone_exact, int reset);
+
 #ifdef __cplusplus
 }
 #endif

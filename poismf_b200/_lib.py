@@ -25,7 +25,7 @@ SYMBOLS = [
     "pmf_b200_set_factors", "pmf_b200_get_factors", "pmf_b200_bind_factors", "pmf_b200_factor_ptr",
     "pmf_b200_set_stream", "pmf_b200_sweeps", "pmf_b200_half_sweep", "pmf_b200_sync",
     "pmf_b200_set_profiling", "pmf_b200_get_profile", "pmf_b200_ipc_export", "pmf_b200_ipc_import",
-    "pmf_b200_run_poismf", "pmf_b200_factors_multiple", "pmf_b200_predict_multiple", "pmf_b200_topN", "pmf_b200_topN_batch",
+    "pmf_b200_run_poismf", "pmf_b200_factors_multiple", "pmf_b200_predict_multiple", "pmf_b200_topN", "pmf_b200_topN_batch", "pmf_b200_topN_stats",
 ]
 
 
@@ -80,6 +80,8 @@ def lib():
     L.pmf_b200_predict_multiple.argtypes = [i, i, vp, vp, vp, vp, vp, sz, i, sz, sz]
     L.pmf_b200_topN.argtypes = [i, i, vp, vp, i, vp, sz, vp, sz, vp, vp, sz, sz]
     L.pmf_b200_topN_batch.argtypes = [i, i, vp, vp, i, vp, sz, sz, vp, vp, vp, vp, sz, sz]
+    L.pmf_b200_topN_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i]
+    L.pmf_b200_topN_stats.restype = None
     _lib = L
     return L
 
@@ -112,6 +114,13 @@ def last_error():
 def require_gpu():
     if lib().pmf_b200_device_count() <= 0:
         raise RuntimeError("poismf_b200: no usable CUDA device (there is no CPU fallback)")
+
+
+def topn_stats(reset=False):
+    """(users scored on tensor cores, users redone exactly) for this thread's topN calls."""
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    lib().pmf_b200_topN_stats(C.byref(a), C.byref(b), int(reset))
+    return a.value, b.value
 
 
 def make_params(method, l2_reg, l1_reg=0.0, w_mult=1.0, step_size=1e-7, limit_step=False, numiter=1,

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -24,6 +25,7 @@
 #include "aux_kernels.cuh"
 #include "kernels.cuh"
 #include "launch.h"
+#include "topn_tc.cuh"
 
 using namespace pmf;
 
@@ -31,6 +33,7 @@ using namespace pmf;
 // errors, counters, interrupt flag
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local unsigned long long g_topn_stats[2] = {0, 0};   // users scored on tensor cores / redone exactly
 static std::atomic<uint64_t> g_launches{0};
 static volatile sig_atomic_t g_interrupted = 0;
 
@@ -1002,7 +1005,7 @@ extern "C" int pmf_b200_predict_multiple(int dtype, int index_bytes, void* out, 
 template <class real, class IX>
 static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_ix, size_t n_users, size_t dimA,
                            const IX* excl_ptr, const IX* excl_ix, IX* outp_ix, real* outp_score, size_t n_top, size_t n,
-                           bool A_is_single_vector)
+                           bool A_is_single_vector, bool allow_tc = true)
 {
     CK(cudaSetDevice(env_device()));
     if (n_top == 0 || n_top > n) return 2;
@@ -1018,12 +1021,36 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
     void* tmp = nullptr;
     std::vector<int> h_ids(chunk * n_top);
     std::vector<real> h_sc(chunk * n_top);
+    // tensor-core candidate scorer (topn_tc.cuh): float, k <= 128, n_top <= 128, non-negative factors
+    bool use_tc = allow_tc && std::is_same<real, float>::value && k <= 128 && n_top <= 128 && n >= 256 &&
+                  !getenv("POISMF_B200_TOPN_EXACT");
+    const int kpad = round_up(k, 8);
+    const int M_cand = (int)std::min<size_t>(n, std::min<size_t>(256, std::max<size_t>(2 * n_top, n_top + 32)));
+    long long* d_out_ids = nullptr; float* d_out_sc = nullptr; int* d_flag = nullptr; int* d_neg = nullptr;
+    std::vector<size_t> redo;          // users whose TF32 proof failed: redone exactly afterwards
     auto body = [&]() -> int {
         const size_t rowsA = A_is_single_vector ? 1 : dimA;
         CK(cudaMalloc(&dB, n * pitch)); CK(cudaMalloc(&dA, rowsA * pitch));
         CK(cudaMemcpy2D(dB, pitch, B, w, w, n, cudaMemcpyHostToDevice));
         CK(cudaMemset(dA, 0, rowsA * pitch));
         CK(cudaMemcpy2D(dA, pitch, A, w, w, rowsA, cudaMemcpyHostToDevice));
+        if (use_tc) {
+            CK(cudaMalloc(&d_neg, sizeof(int)));
+            CK(cudaMemset(d_neg, 0, sizeof(int)));
+            tc::any_negative_kernel<<<256, 256>>>((const float*)dB, n * (size_t)ldf, d_neg);
+            tc::any_negative_kernel<<<256, 256>>>((const float*)dA, rowsA * (size_t)ldf, d_neg);
+            LAUNCHED(); LAUNCHED();
+            int neg = 0;
+            CK(cudaMemcpy(&neg, d_neg, sizeof(int), cudaMemcpyDeviceToHost));
+            if (neg) use_tc = false;      // the TF32 error bound below assumes non-negative factors
+        }
+        if (use_tc) {
+            CK(cudaMalloc(&d_out_ids, chunk * n_top * sizeof(long long)));
+            CK(cudaMalloc(&d_out_sc, chunk * n_top * sizeof(float)));
+            CK(cudaMalloc(&d_flag, chunk * sizeof(int)));
+            CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kpad * 1024));
+        }
         CK(cudaMalloc(&dAsel, chunk * pitch));
         CK(cudaMalloc(&sc_in, chunk * n * sizeof(real))); CK(cudaMalloc(&sc_out, chunk * n * sizeof(real)));
         CK(cudaMalloc(&id_in, chunk * n * sizeof(int))); CK(cudaMalloc(&id_out, chunk * n * sizeof(int)));
@@ -1052,8 +1079,14 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             CK(cudaMemcpy(dusers, hu.data(), m * sizeof(long long), cudaMemcpyHostToDevice));
             gather_rows_kernel<real><<<(int)std::min<size_t>((m * ldf + 255) / 256, 4096), 256>>>(dA, dusers, (int)m, ldf, dAsel);
             LAUNCHED();
-            dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 1024), (unsigned)m);
-            score_items_kernel<real><<<grid, 256, (size_t)ldf * sizeof(real)>>>(dAsel, dB, n, k, ldf, sc_in, id_in);
+            if (use_tc) {
+                dim3 tgrid((unsigned)((n + tc::TN - 1) / tc::TN), (unsigned)((m + tc::TM - 1) / tc::TM));
+                tc::score_tiles_tf32_kernel<<<tgrid, 128, (size_t)kpad * 1024>>>(
+                    (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, (float*)sc_in, id_in);
+            } else {
+                dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 1024), (unsigned)m);
+                score_items_kernel<real><<<grid, 256, (size_t)ldf * sizeof(real)>>>(dAsel, dB, n, k, ldf, sc_in, id_in);
+            }
             LAUNCHED();
             if (dexp) {
                 dim3 g2(8, (unsigned)m);
@@ -1064,6 +1097,24 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             CK(cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp, tmp_bytes, sc_in, sc_out, id_in, id_out,
                                                                   (int)(m * n), (int)m, seg, seg + 1));
             LAUNCHED();
+            if (use_tc) {
+                // exact FP32 re-score of the best M TF32 candidates, final order, and the proof that
+                // nothing outside the candidates can reach the top n_top
+                tc::rescore_select_kernel<<<(unsigned)m, 128>>>((const float*)dAsel, (const float*)dB, k, ldf, id_out,
+                                                                (const float*)sc_out, n, M_cand, M_cand >= (int)n ? 1 : 0,
+                                                                (int)n_top, 4e-3f, d_out_ids, d_out_sc, d_flag);
+                LAUNCHED();
+                CK(cudaGetLastError());
+                std::vector<long long> hid(m * n_top); std::vector<float> hsc(m * n_top); std::vector<int> hfl(m);
+                CK(cudaMemcpy(hid.data(), d_out_ids, m * n_top * sizeof(long long), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hsc.data(), d_out_sc, m * n_top * sizeof(float), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hfl.data(), d_flag, m * sizeof(int), cudaMemcpyDeviceToHost));
+                for (size_t i = 0; i < m * n_top; i++) outp_ix[u0 * n_top + i] = (IX)hid[i];
+                if (outp_score) for (size_t i = 0; i < m * n_top; i++) outp_score[u0 * n_top + i] = (real)hsc[i];
+                for (size_t u = 0; u < m; u++) if (hfl[u]) redo.push_back(u0 + u);
+                g_topn_stats[0] += m;
+                continue;
+            }
             CK(cudaMemcpy2D(h_ids.data(), n_top * sizeof(int), id_out, n * sizeof(int), n_top * sizeof(int), m, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy2D(h_sc.data(), n_top * sizeof(real), sc_out, n * sizeof(real), n_top * sizeof(real), m, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < m * n_top; i++) outp_ix[u0 * n_top + i] = (IX)h_ids[i];
@@ -1071,9 +1122,34 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
         }
         return 0;
     };
-    const int rc = body();
+    int rc = body();
     cudaFree(dB); cudaFree(dA); cudaFree(dAsel); cudaFree(sc_in); cudaFree(sc_out); cudaFree(id_in);
     cudaFree(id_out); cudaFree(seg); cudaFree(dusers); cudaFree(dexp); cudaFree(dexi); cudaFree(tmp);
+    cudaFree(d_out_ids); cudaFree(d_out_sc); cudaFree(d_flag); cudaFree(d_neg);
+    // users whose candidate set could not be proven complete: exact scorer, one call for all of them
+    if (!rc && !redo.empty()) {
+        const size_t R = redo.size();
+        g_topn_stats[1] += R;
+        std::vector<IX> ru(R), rptr(R + 1, 0), rix;
+        for (size_t i = 0; i < R; i++) {
+            const size_t u = redo[i];
+            ru[i] = A_is_single_vector ? (IX)0 : (user_ix ? user_ix[u] : (IX)u);
+            if (excl_ptr && excl_ix) {
+                for (size_t t = (size_t)excl_ptr[u]; t < (size_t)excl_ptr[u + 1]; t++) rix.push_back(excl_ix[t]);
+            }
+            rptr[i + 1] = (IX)rix.size();
+        }
+        std::vector<IX> rout(R * n_top);
+        std::vector<real> rsc(outp_score ? R * n_top : 0);
+        rc = topn_batch_impl<real, IX>(A, B, k, A_is_single_vector ? nullptr : ru.data(), R, dimA,
+                                       (excl_ptr && excl_ix) ? rptr.data() : nullptr,
+                                       (excl_ptr && excl_ix) ? (rix.empty() ? rptr.data() : rix.data()) : nullptr,
+                                       rout.data(), outp_score ? rsc.data() : nullptr, n_top, n, A_is_single_vector, false);
+        for (size_t i = 0; i < R && !rc; i++) {
+            memcpy(outp_ix + redo[i] * n_top, &rout[i * n_top], n_top * sizeof(IX));
+            if (outp_score) memcpy(outp_score + redo[i] * n_top, &rsc[i * n_top], n_top * sizeof(real));
+        }
+    }
     return rc;
 }
 
@@ -1120,6 +1196,13 @@ extern "C" int pmf_b200_topN(int dtype, int index_bytes, const void* a_vec, cons
     if (dtype == PMF_F64 && index_bytes == 8) return topn_single_impl((const double*)a_vec, (const double*)B, k, (const uint64_t*)include_ix, n_include, (uint64_t*)exclude_ix, n_exclude, (uint64_t*)outp_ix, (double*)outp_score, n_top, n);
     if (dtype == PMF_F64 && index_bytes == 4) return topn_single_impl((const double*)a_vec, (const double*)B, k, (const int*)include_ix, n_include, (int*)exclude_ix, n_exclude, (int*)outp_ix, (double*)outp_score, n_top, n);
     return fail("topN: bad dtype/index width");
+}
+
+extern "C" void pmf_b200_topN_stats(unsigned long long* tensor_core_users, unsigned long long* redone_exact, int reset)
+{
+    if (tensor_core_users) *tensor_core_users = g_topn_stats[0];
+    if (redone_exact) *redone_exact = g_topn_stats[1];
+    if (reset) g_topn_stats[0] = g_topn_stats[1] = 0;
 }
 
 extern "C" int pmf_b200_topN_batch(int dtype, int index_bytes, const void* A, const void* B, int k,

@@ -429,3 +429,32 @@ def test_factors_multiple_matches_oracle(dtype, case):
             A = c_funs._predict_factors_multiple(B, Bsum, Amean, csr[1], csr[2], csr[0], method=method, **kw)
             gate = 1e-5 if dtype == np.float64 else 1e-3
             assert (row_rel_err(A, Ar) > gate).mean() <= 0.002
+
+
+# ---------------------------------------------------------------- batched topN on the tensor cores
+@pytest.mark.parametrize("k,n_top", [(64, 100), (50, 10), (7, 37)])
+def test_topn_batch_tensor_core_path_is_exact(k, n_top):
+    """The tcgen05/TF32 scorer only proposes candidates; rankings must equal the exact FP32 ones
+    (ids identical wherever the exact scores are not tied) and most users must NOT need the exact
+    fallback.  Items 30k, users 300, per-user exclusion lists."""
+    from poismf_b200 import _lib, c_funs
+    rng = np.random.default_rng(11)
+    n_items, n_users = 30_000, 300
+    A = np.ascontiguousarray(rng.gamma(0.5, 0.5, size=(n_users, k)).astype(np.float32))
+    B = np.ascontiguousarray(rng.gamma(0.5, 0.5, size=(n_items, k)).astype(np.float32))
+    lens = rng.integers(0, 300, n_users)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    eix = np.concatenate([np.sort(rng.choice(n_items, int(m), replace=False)) for m in lens]).astype(np.uint64)
+    _lib.topn_stats(reset=True)
+    ix, sc = c_funs._topN_batch(A, B, excl_ptr=ptr, excl_ix=eix, top_n=n_top, output_score=True)
+    n_tc, n_redo = _lib.topn_stats(reset=True)
+    assert n_tc == n_users, "tensor-core scorer was not used"
+    assert n_redo <= 0.1 * n_users, f"{n_redo} of {n_users} users fell back to the exact scorer"
+    orc = Restatement(np.float32)
+    for u in range(0, n_users, 7):
+        ex = eix[int(ptr[u]):int(ptr[u + 1])]
+        rc, ix_r, sc_r = orc.topN(np.ascontiguousarray(A[u]), B, n_top, exclude=ex if ex.size else None)
+        assert rc == 0 and np.array_equal(sc[u], sc_r)                 # exact FP32 scores, reference bits
+        diff = np.nonzero(ix[u] != ix_r)[0]
+        assert all((sc_r == sc_r[t]).sum() > 1 for t in diff), "ranking differs outside score ties"
+        assert not np.isin(ix[u], ex).any()
