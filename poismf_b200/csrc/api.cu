@@ -488,7 +488,8 @@ template <class real> struct HandleT : pmf_b200_handle {
             // per-CTA scratch for the three per-non-zero arrays of rows that are not staged
             const long long per_cta = (gb.max_nnz + gb.cluster - 1) / gb.cluster;
             S.gs_stride = (long long)round_up_sz((size_t)per_cta + 4, 4);
-            S.gs_ctas = gb.cluster > 1 ? num_sms
+            // streaming clusters are compiled for two CTAs per SM: scratch for 2 x SMs CTAs
+            S.gs_ctas = gb.cluster > 1 ? 2 * num_sms
                                        : (int)std::min<size_t>(gb.rows.size(), (size_t)num_sms);
             CK(cudaMalloc(&S.gscratch, (size_t)S.gs_ctas * 3 * S.gs_stride * sizeof(real)));
         }
