@@ -278,8 +278,14 @@ def main():
         avg_ms = top["ms"] / max(top["launches"], 1)
         achieved = bytes_launch / (avg_ms / 1e3) / 1e9 if avg_ms > 0 else 0.0
         sweep_bytes = algorithmic_bytes(nnz, dimA, dimB, k, s) + algorithmic_bytes(nnz, dimB, dimA, k, s)
+        traffic = None
+        try:   # DRAM bytes of this launch from the committed ncu --set full capture of the same command
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(f"side{top['side']}_{team_name(top['block_team'])}_cap{top['cap']}")
+        except Exception:
+            pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": which,
+                "traffic": traffic, "peak_source": which,
                 "kernel": f"rows_{team_name(top['block_team'])}_kernel<{cfg['method']}> side="
                           f"{'CSR(A)' if top['side'] == 0 else 'CSC(B)'} cap={top['cap']} rows={top['nrows']} nnz={top['nnz']}",
                 "kernel_avg_ms": avg_ms, "kernel_share_of_step": top["ms"] / max(ms_profiled_pass, 1e-9),
