@@ -85,6 +85,7 @@ struct Bin {
     int cluster = 1;        // > 1: a thread-block cluster of this many CTAs per row
     int width = 32;         // lanes per row for the warp-level bins
     int cap = 0;            // staged tile capacity; 0 = tile stays in global memory
+    int acap = -1;          // capacity of the per-non-zero arrays kept in shared memory (-1: == cap)
     int threads = 256;
     size_t slice = 0, smem = 0;
     std::vector<int> rows;  // local row ids, longest first
@@ -431,7 +432,8 @@ template <class real> struct HandleT : pmf_b200_handle {
             }
             Bin b;     // beyond 16 resident slices: 16 CTAs, each streaming its slice from L2
             b.block = true; b.cluster = 16; b.cap = 0; b.threads = thr;
-            b.slice = slice_bytes(thr, nvec, 0) + GANG_XBYTES;
+            b.acap = 4096;   // 64 KB (float) of per-non-zero arrays on chip; two such CTAs share an SM
+            b.slice = slice_bytes(thr, nvec, 0) + GANG_XBYTES + (size_t)4 * b.acap * sizeof(real);
             b.smem = b.slice;
             bins.push_back(b);
         } else {   // strict numerics: everything longer stays on one CTA, tile in global memory / L2
@@ -604,8 +606,9 @@ template <class real> struct HandleT : pmf_b200_handle {
             P.rows = b.d_rows; P.nrows = (int)b.rows.size();
             P.counter = counters + bi;
             P.k = k; P.kp = kp; P.ldf = ldf; P.cap = b.cap; P.slice_bytes = (int)b.slice;
+            P.acap = b.acap < 0 ? b.cap : b.acap;
             P.hc = hc;
-            P.gscratch = b.cap == 0 ? S.gscratch : nullptr;
+            P.gscratch = b.cap == 0 ? S.gscratch : nullptr;   // rows beyond acap per CTA fall back to global arrays
             P.gs_stride = S.gs_stride;
             P.n_unchanged = d_unchanged;
             const int wm = updA ? 0 : 1;

@@ -33,6 +33,8 @@ template <class real> struct SideParams {
     int* counter;          // dynamic fetch counter (zeroed before the launch)
     int k, kp, ldf;
     int cap;               // tile capacity (non-zeros) of a team's shared slice; 0: tile stays in global
+    int acap;              // capacity of the per-non-zero arrays (x, <x,F>, coefficients, <d,F>) in the slice;
+                           // == cap for staged bins; > 0 with cap == 0: tile streamed, arrays kept on chip
     int slice_bytes;       // shared bytes per team
     HalfSweepConsts<real> hc;
     real* gscratch;        // per-CTA global scratch for rows that are not staged (3*gs_stride reals)
@@ -58,14 +60,15 @@ template <class real> struct Slice {
     real* vecs;
     real *xv, *pa, *pb, *pc;
     real* tile;
-    PMF_DEVINL Slice(unsigned char* base, int team_size, int nvec, int kp, int cap, bool gang = false)
+    PMF_DEVINL Slice(unsigned char* base, int team_size, int nvec, int kp, int cap, bool gang = false, int acap = -1)
     {
+        if (acap < 0) acap = cap;
         team_scratch = base; if (team_size > 32) base += 640;   // (sub-)warp teams reduce by shuffles only
         xchg = base; if (gang) base += GANG_XBYTES;
         gscr = (real*)base; base += (size_t)team_size * 16;
         vecs = (real*)base; base += (size_t)nvec * kp * sizeof(real);
-        xv = (real*)base; pa = xv + cap; pb = pa + cap; pc = pb + cap;
-        base += (size_t)4 * cap * sizeof(real);
+        xv = (real*)base; pa = xv + acap; pb = pa + acap; pc = pb + acap;
+        base += (size_t)4 * acap * sizeof(real);
         tile = (real*)base;
     }
 };
@@ -94,6 +97,11 @@ PMF_DEVINL void process_row(const Team& tm, const SideParams<real>& P, const Sli
     if (P.cap > 0 && n <= P.cap) {
         rv.tile = S.tile; rv.xv = S.xv; rv.pa = S.pa; rv.pb = S.pb; rv.pc = S.pc;
         stage_tile(tm, P.F, rv.ind, P.xv + beg, n, P.ldf, kp, S.tile, S.xv, reinterpret_cast<int*>(S.pa));
+    } else if (n <= P.acap) {
+        // tile streamed from L2, but the per-non-zero arrays (read by every line-search trial) on chip
+        rv.tile = nullptr; rv.xv = S.xv; rv.pa = S.pa; rv.pb = S.pb; rv.pc = S.pc;
+        for (int t = tm.rank(); t < n; t += tm.size()) S.xv[t] = P.xv[beg + t];
+        tm.sync();
     } else {
         rv.tile = nullptr; rv.xv = P.xv + beg;
         rv.pa = gscratch_cta; rv.pb = gscratch_cta + P.gs_stride; rv.pc = gscratch_cta + 2 * P.gs_stride;
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(256, PMF_WARP_KERNEL_MIN_CTAS) rows_warp_kerne
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int team_id = threadIdx.x / W;
-    Slice<real> S(smem + (size_t)team_id * P.slice_bytes, W, num_vecs(METHOD), P.kp, P.cap);
+    Slice<real> S(smem + (size_t)team_id * P.slice_bytes, W, num_vecs(METHOD), P.kp, P.cap, false, P.acap);
     SubWarpTeam<W> tm(S.team_scratch);
     for (;;) {
         int idx = 0;
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) rows_block_ke
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int next_row;
-    Slice<real> S(smem, blockDim.x, num_vecs(METHOD), P.kp, P.cap);
+    Slice<real> S(smem, blockDim.x, num_vecs(METHOD), P.kp, P.cap, false, P.acap);
     BlockTeam tm(S.team_scratch);
     real* gs = P.gscratch ? P.gscratch + (size_t)blockIdx.x * 3 * P.gs_stride : nullptr;
     for (;;) {
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(512, MINB) rows_cluster_kernel(const SideParam
 {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cl = cg::this_cluster();
-    Slice<real> S(smem, blockDim.x, num_vecs(METHOD), P.kp, P.cap, true);
+    Slice<real> S(smem, blockDim.x, num_vecs(METHOD), P.kp, P.cap, true, P.acap);
     ClusterTeam tm(S.team_scratch, S.xchg);
     __shared__ int next_row;
     real* gs = P.gscratch ? P.gscratch + (size_t)blockIdx.x * 3 * P.gs_stride : nullptr;

@@ -458,3 +458,34 @@ def test_topn_batch_tensor_core_path_is_exact(k, n_top):
         diff = np.nonzero(ix[u] != ix_r)[0]
         assert all((sc_r == sc_r[t]).sum() > 1 for t in diff), "ranking differs outside score ties"
         assert not np.isin(ix[u], ex).any()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_very_heavy_columns_streaming_clusters(dtype):
+    """A handful of items with ~1e4 non-zeros each: every column is a 16-CTA cluster row whose slices
+    are streamed from L2 (the cap-0 bin) in double, staged-or-streamed in float.  cg and tncg, fast
+    numerics, against the oracle's log-likelihood; pg bit-exact in strict mode (single-CTA path)."""
+    from poismf_b200.synth import init_factors, powerlaw_counts
+    dimA, dimB, k = 30_000, 40, 50
+    csr, csc = powerlaw_counts(dimA, dimB, 500_000, alpha_a=0.3, alpha_b=0.3, dtype=dtype, seed=9)
+    assert np.diff(csc[1].astype(np.int64)).max() > 8_000
+    A0, B0 = init_factors(dimA, dimB, k, dtype=dtype)
+    orc = Restatement(dtype)
+    for method, kw, gate in (("cg", dict(l2_reg=1e3, maxupd=5, numiter=2, limit_step=True), 1e-4),
+                             ("tncg", dict(l2_reg=1e2, maxupd=15 * k, numiter=1), 1e-4)):
+        Ar, Br = _oracle(dtype, csr, csc, A0, B0, method, kw)
+        A, B = A0.copy(), B0.copy()
+        assert run_device(csr, csc, A, B, method, kw) == 0
+        assert np.isfinite(A).all() and np.isfinite(B).all() and (A >= 0).all() and (B >= 0).all()
+        l_ref, l_dev = orc.llk(Ar, Br, csr), orc.llk(A, B, csr)
+        g = gate if dtype == np.float64 else 2e-2
+        assert abs(l_dev - l_ref) <= g * abs(l_ref), (method, l_dev, l_ref)
+    kw = dict(l2_reg=1e6, step_size=1e-6, maxupd=2, numiter=2)
+    Ar, Br = _oracle(dtype, csr, csc, A0, B0, "pg", kw)
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, "pg", kw, flags=FLAG_STRICT) == 0
+    assert np.array_equal(A, Ar) and np.array_equal(B, Br)
+    A, B = A0.copy(), B0.copy()
+    assert run_device(csr, csc, A, B, "pg", kw) == 0
+    gate = 1e-5 if dtype == np.float64 else 1e-3
+    assert row_rel_err(A, Ar).max() <= gate and row_rel_err(B, Br).max() <= gate
