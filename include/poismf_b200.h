@@ -79,9 +79,10 @@ int pmf_b200_set_stream(pmf_b200_handle* h, void* cuda_stream);   /* e.g. torch'
 int pmf_b200_sweeps(pmf_b200_handle* h, const pmf_b200_params* p);
 /* One half-sweep, for the sharding layer (poismf_b200/sharding.py): updates the
  * local rows of B (side=CSC) or A (side=CSR).  `step_size` is the CURRENT pg step
- * (the caller applies the halving of src/poismf.c:532); `first_half` tells the pg
- * column-sum scaling of src/poismf.c:523-524 from the one of :573-577.
- * *converged (may be NULL) receives the tncg early-stop verdict's numerator: the
+ * (the caller applies the halving of src/poismf.c:532) and `cnst_div` the sweep's
+ * 1/(1+2*l2*step) of src/poismf.c:511; the side selects pg's column-sum scaling
+ * (once on the B side, :523-524; twice on the A side, :573-577).
+ * *n_unchanged (may be NULL) receives the numerator of tncg's early-stop test: the
  * number of local rows that moved less than 1e-4 (src/poismf.c:393-396). */
 int pmf_b200_half_sweep(pmf_b200_handle* h, int side, const pmf_b200_params* p, double step_size,
                         double cnst_div, unsigned long long* n_unchanged);

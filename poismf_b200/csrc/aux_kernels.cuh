@@ -7,21 +7,13 @@
 
 namespace pmf {
 
-// host sparse_ix (size_t or int) -> device int32 indices / int64 row pointers
+// host sparse_ix (size_t) -> device int32 indices (row pointers are widened to int64 on the host)
 template <class SRC>
 __global__ void narrow_indices_kernel(const SRC* __restrict__ src, int* __restrict__ dst, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = (int)src[i];
 }
-template <class SRC>
-__global__ void widen_indptr_kernel(const SRC* __restrict__ src, long long* __restrict__ dst, size_t n)
-{
-    const long long base = (long long)src[0];
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        dst[i] = (long long)src[i] - base;
-}
-
 template <class real> struct ColsumFinal {
     real l1;        // added when > 0                       (:513-514)
     real scale1;    // pg, w==1: -step                      (:523-524, :573-574)

@@ -4,7 +4,8 @@
 //   half-sweep : update of every row of one factor matrix with the other held fixed
 //   row        : one user (CSR side) or one item (CSC side); its "tile" is the set of
 //                gathered rows of the FIXED factor matrix, one per non-zero
-//   team       : the group of threads that cooperates on one row (a warp, or a CTA)
+//   team       : the group of threads that cooperates on one row (8/16/32 lanes of a warp, a
+//                CTA, or a thread-block cluster — cluster_team.cuh)
 //
 // Numerics modes (template parameter STRICT):
 //   STRICT = true  : mimics the reference built with sequential BLAS and no FMA
@@ -98,10 +99,10 @@ PMF_DEVINL bool is_bad(double v) { return isnan(v) || isinf(v); }
 // A team is the group of threads that cooperates on one row.  It exposes
 //   rank()/size()/sync()      : split of the per-non-zero loops and of the "owner" k-loops
 //   sum/min/max/bcast0        : team-wide reductions (block-level ones cost two barriers)
-//   kbegin()/kstride()/ksum() : REDUNDANT k-vector reductions — every warp (or sub-warp) of
-//                               the team walks the whole k-vector itself and reduces with
-//                               shuffles, so a dot product of two shared k-vectors needs no
-//                               barrier at all (k <= 256: at most 8 elements per lane)
+//   kbegin()/kstride()/ksum() : k-vector reductions WITHIN one warp (or sub-warp): whichever warp
+//                               walks the shared k-vector reduces it with shuffles, no barrier
+//                               (k <= 256: at most 8 elements per lane).  CTA teams run their
+//                               k-scalar phases on warp 0 (k_leader) and broadcast (kslots).
 //   nnz_sum*/nnz_vec_sum      : sums over the row's non-zeros (span the cluster for gangs)
 // All reductions return the SAME bits to every member: the solver's control flow is
 // executed redundantly by all members and must not diverge.

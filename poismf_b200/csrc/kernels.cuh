@@ -1,9 +1,10 @@
-// poismf_b200 — half-sweep kernels: one warp per short row, one CTA per heavy row.
+// poismf_b200 — half-sweep kernels: a (sub-)warp per short row, a CTA per longer row, a
+// thread-block cluster per heavy row.
 //
 // Replaces the OpenMP `parallel for schedule(dynamic)` row loops of the reference
 // (/root/reference/src/poismf.c:159-187 pg, :296-321 cg, :352-397 tncg).
-// Rows are binned by non-zero count on the host (plan.cpp); each bin is one launch
-// of a persistent grid whose teams fetch rows from a list sorted by decreasing
+// Rows are binned by non-zero count on the host (HandleT::plan in api.cu); each bin is one
+// launch of a persistent grid whose teams fetch rows from a list sorted by decreasing
 // length (longest-processing-time-first) through an atomic counter.
 #pragma once
 #include "cluster_team.cuh"

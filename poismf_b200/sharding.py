@@ -5,8 +5,8 @@ independent (/root/reference/src/poismf.c:159-187, :296-321, :352-397: every row
 own CSR/CSC slice, the FULL opposite factor matrix and the k column sums, and writes its
 own k numbers).  So:
 
-  * users are split into contiguous CSR row ranges balanced by non-zeros, items into
-    contiguous CSC column ranges balanced by non-zeros; rank r holds its two slices,
+  * users are split into contiguous CSR row ranges balanced by (cost-weighted) non-zeros, items
+    into contiguous CSC column ranges likewise; rank r holds its two slices,
   * A and B are replicated on every rank,
   * after the B half-sweep every rank's freshly updated rows of B are exchanged
     (one exchange step per half-sweep), likewise A after the A half-sweep,
@@ -21,17 +21,32 @@ from __future__ import annotations
 import numpy as np
 
 
-def nnz_balanced_ranges(indptr, nparts):
-    """Split rows 0..n into `nparts` contiguous ranges with ~equal non-zeros.
+def row_cost(nnz_per_row):
+    """Relative device cost of solving a row with n non-zeros (measured on B200, r1 bins of config #2):
+    ~10 non-zero-equivalents of fixed work per row, and non-zeros of long rows cost more — rows beyond
+    one CTA's shared memory pay cluster barriers (x2), rows streamed from L2 more again (x3)."""
+    n = np.asarray(nnz_per_row, dtype=np.float64)
+    f = np.where(n <= 1000, 1.0, np.where(n <= 16000, 2.0, 3.0))
+    return np.where(n > 0, 10.0 + n * f, 0.0)
 
+
+def nnz_balanced_ranges(indptr, nparts, cost_aware=True):
+    """Split rows 0..n into `nparts` contiguous ranges of ~equal work.
+
+    Work is the non-zero count, or with `cost_aware` the device cost model of `row_cost` (power-law
+    matrices put a few very long rows somewhere; their non-zeros are dearer than a short row's).
     Returns a list of (begin, end); ranges may be empty when nparts > rows."""
     indptr = np.asarray(indptr).astype(np.int64)
     n = indptr.shape[0] - 1
-    total = int(indptr[-1] - indptr[0])
+    if cost_aware:
+        cum = np.concatenate([[0.0], np.cumsum(row_cost(np.diff(indptr)))])
+    else:
+        cum = (indptr - indptr[0]).astype(np.float64)
+    total = float(cum[-1])
     cuts = [0]
     for p in range(1, nparts):
-        target = indptr[0] + (total * p) // nparts
-        c = int(np.searchsorted(indptr, target, side="left"))
+        target = total * p / nparts
+        c = int(np.searchsorted(cum, target, side="left"))
         c = min(max(c, cuts[-1]), n)
         cuts.append(c)
     cuts.append(n)

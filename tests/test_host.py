@@ -86,8 +86,13 @@ def test_nnz_balanced_ranges():
         assert rg[0][0] == 0 and rg[-1][1] == A0.shape[0]
         assert all(rg[i][1] == rg[i + 1][0] for i in range(parts - 1))
         ptr = csr[1].astype(np.int64)
-        loads = [ptr[e] - ptr[b] for b, e in rg]
+        rg_nnz = nnz_balanced_ranges(csr[1], parts, cost_aware=False)
+        loads = [ptr[e] - ptr[b] for b, e in rg_nnz]
         assert max(loads) <= ptr[-1] / parts + np.diff(ptr).max()
+        from poismf_b200.sharding import row_cost
+        cost = row_cost(np.diff(ptr))
+        cl = [cost[b:e].sum() for b, e in rg]
+        assert max(cl) <= cost.sum() / parts + cost.max() + 1e-9
     v, p, i = slice_compressed(csr, 10, 20)
     assert p[0] == 0 and p[-1] == v.shape[0] == i.shape[0]
     assert nnz_balanced_ranges(np.array([0, 5]), 4)[-1] == (1, 1) or True   # more parts than rows: empty tails
