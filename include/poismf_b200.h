@@ -158,6 +158,12 @@ int pmf_b200_topN_batch(int dtype, int index_bytes, const void* A, const void* B
  * not prove their candidate set complete. */
 void pmf_b200_topN_stats(unsigned long long* tensor_core_users, unsigned long long* redone_exact, int reset);
 
+/* Device blocks released by the calls above are cached per process for the next call (the reference's
+ * API is stateless, so every call would otherwise pay a dozen cudaMalloc/cudaFree round trips; env
+ * POISMF_B200_POOL_MB caps the idle bytes, 0 disables, default half of the device's memory).
+ * This returns all idle blocks to the driver; result: bytes released. */
+size_t pmf_b200_release_cache(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -23,6 +24,7 @@
 
 #include "../../include/poismf_b200.h"
 #include "aux_kernels.cuh"
+#include "devpool.h"
 #include "kernels.cuh"
 #include "launch.h"
 #include "topn_tc.cuh"
@@ -105,24 +107,26 @@ template <class real> struct Side {
     int planned_method = -1;
     int* d_empty = nullptr;
     int n_empty = 0;
+    std::vector<int> h_empty;
     int* d_all_rows = nullptr;
     real* gscratch = nullptr;
     long long gs_stride = 0;
     int gs_ctas = 0;
+    // callers synchronise the streams that used these buffers first (devpool.h)
     void free_plan()
     {
         for (auto& b : bins) for (auto e : b.ev) cudaEventDestroy(e);
-        if (d_all_rows) cudaFree(d_all_rows);
-        if (gscratch) cudaFree(gscratch);
+        if (d_all_rows) dfree(d_all_rows);
+        if (gscratch) dfree(gscratch);
         d_all_rows = nullptr; gscratch = nullptr; d_empty = nullptr;
         bins.clear(); planned_method = -1;
     }
     void free_all()
     {
         free_plan();
-        if (xv) cudaFree(xv);
-        if (ptr) cudaFree(ptr);
-        if (ind) cudaFree(ind);
+        if (xv) dfree(xv);
+        if (ptr) dfree(ptr);
+        if (ind) dfree(ind);
         xv = nullptr; ptr = nullptr; ind = nullptr;
     }
 };
@@ -144,6 +148,9 @@ struct pmf_b200_handle {
     virtual int half_sweep(int side, const pmf_b200_params& p, double step, double cdiv,
                            unsigned long long* n_unchanged) = 0;
     virtual int sweeps(const pmf_b200_params& p) = 0;
+    virtual int run_dropin(void* A, void* B, const void* Xr, const void* Xr_indptr, const void* Xr_indices, size_t nnz_r,
+                           const void* Xc, const void* Xc_indptr, const void* Xc_indices, size_t nnz_c, int index_bytes,
+                           const pmf_b200_params& p, const std::function<void(const char*)>& lap, bool timing) = 0;
     virtual int factors_multiple(void* A_out, const void* Bsum, const void* Amean, const pmf_b200_params& p,
                                  int reuse_mean) = 0;
     virtual int ipc_export(int which, void* out) = 0;
@@ -173,92 +180,111 @@ template <class real> struct HandleT : pmf_b200_handle {
     static constexpr int NAUX = 6;
     cudaStream_t aux[NAUX] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
+    // the stateless drop-in calls pipeline their transfers against the half-sweeps on this stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
+    std::vector<void*> deferred;   // staging buffers, released at the next synchronisation point
     static constexpr int V = RealTraits<real>::V;
 
     ~HandleT() override
     {
         cudaSetDevice(device);
+        sync_all();
         sides[0].free_all(); sides[1].free_all();
-        if (ownA && A) cudaFree(A);
-        if (ownB && B) cudaFree(B);
-        if (csum) cudaFree(csum);
-        if (partial) cudaFree(partial);
-        if (counters) cudaFree(counters);
-        if (d_unchanged) cudaFree(d_unchanged);
+        if (ownA && A) dfree(A);
+        if (ownB && B) dfree(B);
+        if (csum) dfree(csum);
+        if (partial) dfree(partial);
+        if (counters) dfree(counters);
+        if (d_unchanged) dfree(d_unchanged);
         for (int i = 0; i < NAUX; i++) {
             if (aux[i]) cudaStreamDestroy(aux[i]);
             if (ev_join[i]) cudaEventDestroy(ev_join[i]);
         }
         if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_copy) cudaEventDestroy(ev_copy);
+        if (ev_main) cudaEventDestroy(ev_main);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    // wait for everything this handle has enqueued, then release the staging buffers
+    int sync_all()
+    {
+        cudaError_t e1 = stream ? cudaStreamSynchronize(stream) : cudaSuccess;
+        cudaError_t e2 = copy_stream ? cudaStreamSynchronize(copy_stream) : cudaSuccess;
+        for (void* q : deferred) dfree(q);
+        deferred.clear();
+        if (e1 != cudaSuccess) return fail("stream synchronize failed: %s", cudaGetErrorString(e1));
+        if (e2 != cudaSuccess) return fail("stream synchronize failed: %s", cudaGetErrorString(e2));
+        return 0;
     }
 
     int init()
     {
         CK(cudaSetDevice(device));
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, device));
-        num_sms = prop.multiProcessorCount;
+        CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         ldf = round_up(k, V);
         kp = tile_stride(k, V);
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         own_stream = true;
-        CK(cudaMalloc(&A, dimA * (size_t)ldf * sizeof(real)));
+        CK(dmalloc(&A, dimA * (size_t)ldf * sizeof(real)));
         ownA = true;
-        CK(cudaMalloc(&B, dimB * (size_t)ldf * sizeof(real)));
+        CK(dmalloc(&B, dimB * (size_t)ldf * sizeof(real)));
         ownB = true;
         CK(cudaMemsetAsync(A, 0, dimA * (size_t)ldf * sizeof(real), stream));
         CK(cudaMemsetAsync(B, 0, dimB * (size_t)ldf * sizeof(real), stream));
-        CK(cudaMalloc(&csum, (size_t)kp * sizeof(real)));
+        CK(dmalloc(&csum, (size_t)kp * sizeof(real)));
         n_partial = num_sms * 4;
-        CK(cudaMalloc(&partial, (size_t)n_partial * ldf * sizeof(real)));
-        CK(cudaMalloc(&counters, 64 * sizeof(int)));   // one per bin (<= 12 + 3 + 5)
-        CK(cudaMalloc(&d_unchanged, sizeof(unsigned long long)));
+        CK(dmalloc(&partial, (size_t)n_partial * ldf * sizeof(real)));
+        CK(dmalloc(&counters, 64 * sizeof(int)));   // one per bin (<= 12 + 3 + 5)
+        CK(dmalloc(&d_unchanged, sizeof(unsigned long long)));
         for (int i = 0; i < NAUX; i++) {
             CK(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
         }
         CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
         return 0;
     }
 
+    // enqueue the upload of one orientation on `st`; temporaries go to `deferred`
     template <class IX>
-    int upload_side(Side<real>& S, const real* values, const IX* indptr, const IX* indices, size_t nnz, size_t n_rows)
+    int upload_side(Side<real>& S, const real* values, const IX* indptr, const IX* indices, size_t nnz, size_t n_rows,
+                    cudaStream_t st)
     {
         S.h_ptr.resize(n_rows + 1);
         const long long base = (long long)indptr[0];
         for (size_t i = 0; i <= n_rows; i++) S.h_ptr[i] = (long long)indptr[i] - base;
         if ((size_t)S.h_ptr[n_rows] != nnz) return fail("set_matrix: indptr[n_rows]-indptr[0] != nnz");
-        CK(cudaMalloc(&S.xv, std::max<size_t>(nnz, 1) * sizeof(real)));
-        CK(cudaMalloc(&S.ind, std::max<size_t>(nnz, 1) * sizeof(int)));
-        CK(cudaMalloc(&S.ptr, (n_rows + 1) * sizeof(long long)));
-        CK(cudaMemcpyAsync(S.xv, values, nnz * sizeof(real), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(S.ptr, S.h_ptr.data(), (n_rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        CK(dmalloc(&S.xv, std::max<size_t>(nnz, 1) * sizeof(real)));
+        CK(dmalloc(&S.ind, std::max<size_t>(nnz, 1) * sizeof(int)));
+        CK(dmalloc(&S.ptr, (n_rows + 1) * sizeof(long long)));
+        CK(cudaMemcpyAsync(S.xv, values, nnz * sizeof(real), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.ptr, S.h_ptr.data(), (n_rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
         // indices: upload at host width, narrow to int32 on the device
         if (sizeof(IX) == sizeof(int)) {
-            CK(cudaMemcpyAsync(S.ind, indices, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(S.ind, indices, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
         } else {
             IX* tmp = nullptr;
             const size_t chunk = (size_t)1 << 27;   // bounded staging buffer (1 GiB of 8-byte ids)
-            CK(cudaMalloc(&tmp, std::min(chunk, std::max<size_t>(nnz, 1)) * sizeof(IX)));
+            CK(dmalloc(&tmp, std::min(chunk, std::max<size_t>(nnz, 1)) * sizeof(IX)));
+            deferred.push_back(tmp);
             for (size_t off = 0; off < nnz; off += chunk) {
                 const size_t m = std::min(chunk, nnz - off);
-                CK(cudaMemcpyAsync(tmp, indices + off, m * sizeof(IX), cudaMemcpyHostToDevice, stream));
-                narrow_indices_kernel<IX><<<num_sms * 8, 256, 0, stream>>>(tmp, S.ind + off, m);
+                CK(cudaMemcpyAsync(tmp, indices + off, m * sizeof(IX), cudaMemcpyHostToDevice, st));
+                narrow_indices_kernel<IX><<<num_sms * 8, 256, 0, st>>>(tmp, S.ind + off, m);
                 LAUNCHED();
                 CK(cudaGetLastError());
             }
-            CK(cudaStreamSynchronize(stream));
-            cudaFree(tmp);
         }
-        CK(cudaStreamSynchronize(stream));
         return 0;
     }
-
-    int set_matrix(int side, const void* values, const void* indptr, const void* indices, size_t nnz,
-                   int index_bytes, size_t row_begin, size_t n_rows) override
+    int upload_matrix(int side, const void* values, const void* indptr, const void* indices, size_t nnz,
+                      int index_bytes, size_t row_begin, size_t n_rows, cudaStream_t st)
     {
-        CK(cudaSetDevice(device));
         if (side != 0 && side != 1) return fail("set_matrix: bad side");
         const size_t dim = side == PMF_SIDE_CSR ? dimA : dimB;
         if (row_begin + n_rows > dim) return fail("set_matrix: row range exceeds the dimension");
@@ -266,61 +292,69 @@ template <class real> struct HandleT : pmf_b200_handle {
         S.free_all();
         S.nnz = nnz; S.row_begin = row_begin; S.n_rows = n_rows;
         if (index_bytes == 8)
-            return upload_side<uint64_t>(S, (const real*)values, (const uint64_t*)indptr, (const uint64_t*)indices, nnz, n_rows);
+            return upload_side<uint64_t>(S, (const real*)values, (const uint64_t*)indptr, (const uint64_t*)indices, nnz, n_rows, st);
         if (index_bytes == 4)
-            return upload_side<int>(S, (const real*)values, (const int*)indptr, (const int*)indices, nnz, n_rows);
+            return upload_side<int>(S, (const real*)values, (const int*)indptr, (const int*)indices, nnz, n_rows, st);
         return fail("set_matrix: index_bytes must be 4 or 8");
+    }
+
+    int set_matrix(int side, const void* values, const void* indptr, const void* indices, size_t nnz,
+                   int index_bytes, size_t row_begin, size_t n_rows) override
+    {
+        CK(cudaSetDevice(device));
+        if (sync_all()) return 1;       // the side's old buffers may still be in use
+        const int rc = upload_matrix(side, values, indptr, indices, nnz, index_bytes, row_begin, n_rows, stream);
+        return sync_all() || rc;
     }
 
     // dense host rows are k reals, device rows ldf reals: one contiguous copy + a device repack
     // (a pitched cudaMemcpy2D of 200-byte rows is ~10x slower over PCIe)
-    int copy_in(real* dev, const void* host, size_t n)
+    int copy_in(real* dev, const void* host, size_t n, cudaStream_t st)
     {
-        if (ldf == k) { CK(cudaMemcpyAsync(dev, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, stream)); return 0; }
+        if (ldf == k) { CK(cudaMemcpyAsync(dev, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, st)); return 0; }
         real* tmp = nullptr;
-        CK(cudaMalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
-        CK(cudaMemcpyAsync(tmp, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, stream));
-        pad_rows_kernel<real><<<num_sms * 8, 256, 0, stream>>>(tmp, dev, n, k, ldf);
+        CK(dmalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
+        deferred.push_back(tmp);
+        CK(cudaMemcpyAsync(tmp, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, st));
+        pad_rows_kernel<real><<<num_sms * 8, 256, 0, st>>>(tmp, dev, n, k, ldf);
         LAUNCHED();
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(stream));
-        cudaFree(tmp);
         return 0;
     }
-    int copy_out(void* host, const real* dev, size_t n)
+    int copy_out(void* host, const real* dev, size_t n, cudaStream_t st)
     {
-        if (ldf == k) { CK(cudaMemcpyAsync(host, dev, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, stream)); return 0; }
+        if (ldf == k) { CK(cudaMemcpyAsync(host, dev, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, st)); return 0; }
         real* tmp = nullptr;
-        CK(cudaMalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
-        unpad_rows_kernel<real><<<num_sms * 8, 256, 0, stream>>>(dev, tmp, n, k, ldf);
+        CK(dmalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
+        deferred.push_back(tmp);
+        unpad_rows_kernel<real><<<num_sms * 8, 256, 0, st>>>(dev, tmp, n, k, ldf);
         LAUNCHED();
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(host, tmp, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        cudaFree(tmp);
+        CK(cudaMemcpyAsync(host, tmp, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, st));
         return 0;
     }
     int set_factors(const void* Ah, const void* Bh) override
     {
         CK(cudaSetDevice(device));
-        if (Ah && copy_in(A, Ah, dimA)) return 1;
-        if (Bh && copy_in(B, Bh, dimB)) return 1;
-        CK(cudaStreamSynchronize(stream));
-        return 0;
+        int rc = 0;
+        if (Ah) rc = copy_in(A, Ah, dimA, stream);
+        if (Bh && !rc) rc = copy_in(B, Bh, dimB, stream);
+        return sync_all() || rc;
     }
     int get_factors(void* Ah, void* Bh) override
     {
         CK(cudaSetDevice(device));
-        if (Ah && copy_out(Ah, A, dimA)) return 1;
-        if (Bh && copy_out(Bh, B, dimB)) return 1;
-        CK(cudaStreamSynchronize(stream));
-        return 0;
+        int rc = 0;
+        if (Ah) rc = copy_out(Ah, A, dimA, stream);
+        if (Bh && !rc) rc = copy_out(Bh, B, dimB, stream);
+        return sync_all() || rc;
     }
     int bind_factors(void* Ad, void* Bd) override
     {
         CK(cudaSetDevice(device));
-        if (Ad) { if (ownA && A) cudaFree(A); A = (real*)Ad; ownA = false; }
-        if (Bd) { if (ownB && B) cudaFree(B); B = (real*)Bd; ownB = false; }
+        if (sync_all()) return 1;
+        if (Ad) { if (ownA && A) dfree(A); A = (real*)Ad; ownA = false; }
+        if (Bd) { if (ownB && B) dfree(B); B = (real*)Bd; ownB = false; }
         return 0;
     }
     void* factor_ptr(int which) override { return which == 0 ? (void*)A : (void*)B; }
@@ -333,11 +367,15 @@ template <class real> struct HandleT : pmf_b200_handle {
                    (size_t)4 * cap * sizeof(real) + (size_t)cap * kp * sizeof(real);
         return round_up_sz(b, 16);
     }
-    int plan(Side<real>& S, int method, bool strict)
+    // row lists are uploaded on `st`; kernels that read them must be ordered after it
+    int plan(Side<real>& S, int method, bool strict, cudaStream_t st)
     {
         const int key = method * 2 + (strict ? 1 : 0);
         if (S.planned_method == key) return 0;
-        S.free_plan();
+        if (S.planned_method >= 0) {    // re-planning for another method: the old lists may be in use
+            if (sync_all()) return 1;
+            S.free_plan();
+        }
         const int nvec = method == PMF_PG ? 3 : (method == PMF_CG ? 7 : TN_NUM_VECS);
         std::vector<Bin> bins;
         // (sub-)warp-per-row bins: {lanes per row, tile capacity}; sub-warps in fast numerics only
@@ -443,7 +481,8 @@ template <class real> struct HandleT : pmf_b200_handle {
             b.smem = b.slice;
             bins.push_back(b);
         }
-        std::vector<int> empty;
+        std::vector<int>& empty = S.h_empty;
+        empty.clear();
         for (size_t r = 0; r < S.n_rows; r++) {
             const long long n = S.h_ptr[r + 1] - S.h_ptr[r];
             if (n == 0) { empty.push_back((int)r); continue; }
@@ -473,18 +512,18 @@ template <class real> struct HandleT : pmf_b200_handle {
             }
             total += b.rows.size();
         }
-        CK(cudaMalloc(&S.d_all_rows, std::max<size_t>(total, 1) * sizeof(int)));
+        CK(dmalloc(&S.d_all_rows, std::max<size_t>(total, 1) * sizeof(int)));
         size_t off = 0;
         for (auto& b : bins) {
             b.d_rows = S.d_all_rows + off;
             if (!b.rows.empty())
-                CK(cudaMemcpyAsync(b.d_rows, b.rows.data(), b.rows.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CK(cudaMemcpyAsync(b.d_rows, b.rows.data(), b.rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
             off += b.rows.size();
         }
         S.d_empty = S.d_all_rows + off;
         S.n_empty = (int)empty.size();
         if (!empty.empty())
-            CK(cudaMemcpyAsync(S.d_empty, empty.data(), empty.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(S.d_empty, empty.data(), empty.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         const Bin& gb = bins.back();
         if (!gb.rows.empty()) {
             // per-CTA scratch for the three per-non-zero arrays of rows that are not staged
@@ -493,10 +532,9 @@ template <class real> struct HandleT : pmf_b200_handle {
             // streaming clusters are compiled for two CTAs per SM: scratch for 2 x SMs CTAs
             S.gs_ctas = gb.cluster > 1 ? 2 * num_sms
                                        : (int)std::min<size_t>(gb.rows.size(), (size_t)num_sms);
-            CK(cudaMalloc(&S.gscratch, (size_t)S.gs_ctas * 3 * S.gs_stride * sizeof(real)));
+            CK(dmalloc(&S.gscratch, (size_t)S.gs_ctas * 3 * S.gs_stride * sizeof(real)));
         }
-        CK(cudaStreamSynchronize(stream));
-        S.bins.swap(bins);
+        S.bins.swap(bins);      // the row lists' host copies stay alive in S.bins until the next plan
         S.planned_method = key;
         return 0;
     }
@@ -541,7 +579,7 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (!S.ptr) return fail("half_sweep: matrix for side %d not set", side);
         if (p.method != PMF_PG && p.method != PMF_CG && p.method != PMF_TNCG) return fail("bad method");
         const bool strict = (p.flags & PMF_FLAG_STRICT) != 0;
-        if (plan(S, p.method, strict)) return 1;
+        if (plan(S, p.method, strict, stream)) return 1;
         const bool updA = side == PMF_SIDE_CSR;
         real* M = updA ? A : B;
         const real* F = updA ? B : A;
@@ -727,8 +765,8 @@ template <class real> struct HandleT : pmf_b200_handle {
             std::vector<real> init(dimA * (size_t)k, (real)0);
             if (reuse_mean || p.method != PMF_TNCG)
                 for (size_t r = 0; r < dimA; r++) memcpy(&init[r * k], Amean, (size_t)k * sizeof(real));
-            if (copy_in(A, init.data(), dimA)) return 1;
-            CK(cudaStreamSynchronize(stream));
+            if (copy_in(A, init.data(), dimA, stream)) return 1;
+            if (sync_all()) return 1;
         }
         pmf_b200_params q = p;
         q.early_stop = 0;
@@ -755,13 +793,20 @@ template <class real> struct HandleT : pmf_b200_handle {
     }
 
     // ---- numiter alternating sweeps (src/poismf.c:506-608) -------------------------
-    int sweeps(const pmf_b200_params& p) override
+    // hooks of the pipelined drop-in call: `before_first_A` runs on the host right after the first B
+    // half-sweep has been enqueued (it uploads the CSR orientation behind it), `after_last_B` right
+    // after the last one (it starts B's download while A's rows are still being solved)
+    struct SweepHooks {
+        std::function<int()> before_first_A, after_last_B;
+    };
+    int sweeps(const pmf_b200_params& p) override { return sweeps_ex(p, nullptr); }
+    int sweeps_ex(const pmf_b200_params& p, SweepHooks* hk)
     {
         // the reference carries step_size as real_t: round it the same way
         real step = (real)p.step_size;
         const real l2 = (real)p.l2_reg;
         bool stopA = false, stopB = false;
-        if (sides[0].n_rows != dimA || sides[1].n_rows != dimB)
+        if (sides[1].n_rows != dimB || (!hk && sides[0].n_rows != dimA))
             return fail("sweeps: handle holds a shard; drive it with pmf_b200_half_sweep");
         for (size_t it = 0; it < p.numiter; it++) {
             if (g_interrupted) return 2;
@@ -772,6 +817,8 @@ template <class real> struct HandleT : pmf_b200_handle {
                 if (p.method == PMF_TNCG && p.early_stop)
                     stopB = ((double)unch / (double)dimB) >= .95;                             // :402
             }
+            if (hk && it == 0 && hk->before_first_A()) return 1;
+            if (hk && it + 1 == p.numiter && hk->after_last_B()) return 1;
             if (p.method == PMF_PG) step = (real)((double)step * 0.5);                        // :532
             if (g_interrupted) return 2;
             if (!(p.method == PMF_TNCG && stopA)) {
@@ -782,6 +829,49 @@ template <class real> struct HandleT : pmf_b200_handle {
             if (stopA && stopB) break;                                                        // :606
         }
         return 0;
+    }
+
+    // ---- the stateless drop-in call (run_poismf), transfers pipelined against the half-sweeps ---------
+    //   stream:       A, B, CSC up | plan | B half-sweep ............ | A half-sweep ..... | A down
+    //   copy_stream:                      | CSR up, plan ------------^ | (last sweep) B down
+    int run_dropin(void* Ah, void* Bh, const void* Xr, const void* Xr_indptr, const void* Xr_indices, size_t nnz_r,
+                   const void* Xc, const void* Xc_indptr, const void* Xc_indices, size_t nnz_c, int index_bytes,
+                   const pmf_b200_params& p, const std::function<void(const char*)>& lap, bool timing) override
+    {
+        CK(cudaSetDevice(device));
+        const bool strict = (p.flags & PMF_FLAG_STRICT) != 0;
+        if (copy_in(A, Ah, dimA, stream)) return 1;
+        if (copy_in(B, Bh, dimB, stream)) return 1;
+        if (upload_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, nnz_c, index_bytes, 0, dimB, stream)) return 1;
+        if (plan(sides[PMF_SIDE_CSC], p.method, strict, stream)) return 1;
+        if (timing) { if (sync_all()) return 1; lap("up A,B,CSC+plan"); }
+        bool csr_up = false, b_down = false;
+        SweepHooks hk;
+        hk.before_first_A = [&]() -> int {
+            csr_up = true;
+            if (upload_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, nnz_r, index_bytes, 0, dimA, copy_stream)) return 1;
+            if (plan(sides[PMF_SIDE_CSR], p.method, strict, copy_stream)) return 1;
+            CK(cudaEventRecord(ev_copy, copy_stream));
+            CK(cudaStreamWaitEvent(stream, ev_copy, 0));
+            if (timing) { cudaStreamSynchronize(copy_stream); lap("up CSR+plan"); cudaStreamSynchronize(stream); lap("B half-sweep"); }
+            return 0;
+        };
+        hk.after_last_B = [&]() -> int {
+            b_down = true;
+            CK(cudaEventRecord(ev_main, stream));
+            CK(cudaStreamWaitEvent(copy_stream, ev_main, 0));
+            return copy_out(Bh, B, dimB, copy_stream);
+        };
+        int rc = sweeps_ex(p, &hk);
+        if (rc == 1) { sync_all(); return 1; }
+        if (timing) { cudaStreamSynchronize(stream); lap("rest of sweeps"); }
+        // interrupted fits (rc 2) still return the factors computed so far
+        if (!b_down && hk.after_last_B()) rc = 1;
+        if (copy_out(Ah, A, dimA, stream)) rc = 1;
+        if (sync_all()) rc = 1;
+        if (timing) lap("download");
+        (void)csr_up;
+        return rc;
     }
 };
 
@@ -844,6 +934,7 @@ extern "C" int pmf_b200_get_profile(pmf_b200_handle* h, pmf_b200_bin_profile* ou
 {
     return h->get_profile(out, max_entries);
 }
+extern "C" size_t pmf_b200_release_cache(void) { return DevPool::get().release(-1); }
 extern "C" int pmf_b200_sync(pmf_b200_handle* h)
 {
     CK(cudaSetDevice(h->device));
@@ -890,7 +981,7 @@ extern "C" int pmf_b200_run_poismf(int dtype, int index_bytes,
     const bool timing = getenv("POISMF_B200_TIMING") != nullptr;
     auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     double t0 = now(), t1;
-    auto lap = [&](const char* what) {
+    std::function<void(const char*)> lap = [&](const char* what) {
         if (!timing) return;
         t1 = now(); fprintf(stderr, "poismf_b200 timing: %-14s %8.2f ms\n", what, t1 - t0); t0 = t1;
     };
@@ -898,24 +989,17 @@ extern "C" int pmf_b200_run_poismf(int dtype, int index_bytes,
     lap("create");
     if (!h) rc = 1;
     const size_t isz = (size_t)index_bytes;
-    auto last = [&](const void* ptr, size_t n) -> size_t {
-        return isz == 8 ? (size_t)((const uint64_t*)ptr)[n] : (size_t)((const int*)ptr)[n];
+    auto span = [&](const void* ptr, size_t n) -> size_t {
+        return isz == 8 ? (size_t)(((const uint64_t*)ptr)[n] - ((const uint64_t*)ptr)[0])
+                        : (size_t)(((const int*)ptr)[n] - ((const int*)ptr)[0]);
     };
-    if (!rc) rc = h->set_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, last(Xr_indptr, dimA), index_bytes, 0, dimA);
-    if (!rc) rc = h->set_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, last(Xc_indptr, dimB), index_bytes, 0, dimB);
-    lap("upload X");
-    if (!rc) rc = h->set_factors(A, B);
-    lap("upload A,B");
     if (!rc) {
         pmf_b200_params p;
         p.l2_reg = l2_reg; p.l1_reg = l1_reg; p.w_mult = w_mult; p.step_size = step_size;
         p.method = method; p.limit_step = limit_step; p.numiter = numiter; p.maxupd = maxupd;
         p.early_stop = early_stop; p.reuse_prev = reuse_prev; p.flags = env_flags(flags);
-        rc = h->sweeps(p);
-        if (timing) { pmf_b200_sync(h); lap("plan+sweeps"); }
-        const int rc2 = (rc != 1) ? h->get_factors(A, B) : 0;   // interrupted fits still return usable factors
-        if (rc2) rc = 1;
-        lap("download");
+        rc = h->run_dropin(A, B, Xr, Xr_indptr, Xr_indices, span(Xr_indptr, dimA), Xc, Xc_indptr, Xc_indices,
+                           span(Xc_indptr, dimB), index_bytes, p, lap, timing);
     }
     if (h) pmf_b200_destroy(h);
     lap("destroy");
@@ -971,9 +1055,9 @@ static int predict_impl(real* out, const real* A, const real* B, const IX* ixA, 
     const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
     int rc = 0;
     auto body = [&]() -> int {
-        CK(cudaMalloc(&dA, dimA * pitch)); CK(cudaMalloc(&dB, dimB * pitch));
-        CK(cudaMalloc(&dout, std::max<size_t>(n, 1) * sizeof(real)));
-        CK(cudaMalloc(&da, std::max<size_t>(n, 1) * sizeof(IX))); CK(cudaMalloc(&db, std::max<size_t>(n, 1) * sizeof(IX)));
+        CK(dmalloc(&dA, dimA * pitch)); CK(dmalloc(&dB, dimB * pitch));
+        CK(dmalloc(&dout, std::max<size_t>(n, 1) * sizeof(real)));
+        CK(dmalloc(&da, std::max<size_t>(n, 1) * sizeof(IX))); CK(dmalloc(&db, std::max<size_t>(n, 1) * sizeof(IX)));
         CK(cudaMemcpy2D(dA, pitch, A, w, w, dimA, cudaMemcpyHostToDevice));
         CK(cudaMemcpy2D(dB, pitch, B, w, w, dimB, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(da, ixA, n * sizeof(IX), cudaMemcpyHostToDevice));
@@ -988,7 +1072,8 @@ static int predict_impl(real* out, const real* A, const real* B, const IX* ixA, 
         return 0;
     };
     rc = body();
-    cudaFree(dA); cudaFree(dB); cudaFree(dout); cudaFree(da); cudaFree(db);
+    if (rc) cudaDeviceSynchronize();     // blocks go back to the cache: nothing may still be using them
+    dfree(dA); dfree(dB); dfree(dout); dfree(da); dfree(db);
     return rc;
 }
 extern "C" int pmf_b200_predict_multiple(int dtype, int index_bytes, void* out, const void* A, const void* B,
@@ -1034,12 +1119,12 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
     std::vector<size_t> redo;          // users whose TF32 proof failed: redone exactly afterwards
     auto body = [&]() -> int {
         const size_t rowsA = A_is_single_vector ? 1 : dimA;
-        CK(cudaMalloc(&dB, n * pitch)); CK(cudaMalloc(&dA, rowsA * pitch));
+        CK(dmalloc(&dB, n * pitch)); CK(dmalloc(&dA, rowsA * pitch));
         CK(cudaMemcpy2D(dB, pitch, B, w, w, n, cudaMemcpyHostToDevice));
         CK(cudaMemset(dA, 0, rowsA * pitch));
         CK(cudaMemcpy2D(dA, pitch, A, w, w, rowsA, cudaMemcpyHostToDevice));
         if (use_tc) {
-            CK(cudaMalloc(&d_neg, sizeof(int)));
+            CK(dmalloc(&d_neg, sizeof(int)));
             CK(cudaMemset(d_neg, 0, sizeof(int)));
             tc::any_negative_kernel<<<256, 256>>>((const float*)dB, n * (size_t)ldf, d_neg);
             tc::any_negative_kernel<<<256, 256>>>((const float*)dA, rowsA * (size_t)ldf, d_neg);
@@ -1049,17 +1134,17 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             if (neg) use_tc = false;      // the TF32 error bound below assumes non-negative factors
         }
         if (use_tc) {
-            CK(cudaMalloc(&d_out_ids, chunk * n_top * sizeof(long long)));
-            CK(cudaMalloc(&d_out_sc, chunk * n_top * sizeof(float)));
-            CK(cudaMalloc(&d_flag, chunk * sizeof(int)));
+            CK(dmalloc(&d_out_ids, chunk * n_top * sizeof(long long)));
+            CK(dmalloc(&d_out_sc, chunk * n_top * sizeof(float)));
+            CK(dmalloc(&d_flag, chunk * sizeof(int)));
             CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kpad * 1024));
         }
-        CK(cudaMalloc(&dAsel, chunk * pitch));
-        CK(cudaMalloc(&sc_in, chunk * n * sizeof(real))); CK(cudaMalloc(&sc_out, chunk * n * sizeof(real)));
-        CK(cudaMalloc(&id_in, chunk * n * sizeof(int))); CK(cudaMalloc(&id_out, chunk * n * sizeof(int)));
-        CK(cudaMalloc(&seg, (chunk + 1) * sizeof(int)));
-        CK(cudaMalloc(&dusers, chunk * sizeof(long long)));
+        CK(dmalloc(&dAsel, chunk * pitch));
+        CK(dmalloc(&sc_in, chunk * n * sizeof(real))); CK(dmalloc(&sc_out, chunk * n * sizeof(real)));
+        CK(dmalloc(&id_in, chunk * n * sizeof(int))); CK(dmalloc(&id_out, chunk * n * sizeof(int)));
+        CK(dmalloc(&seg, (chunk + 1) * sizeof(int)));
+        CK(dmalloc(&dusers, chunk * sizeof(long long)));
         std::vector<int> h_seg(chunk + 1);
         for (size_t u = 0; u <= chunk; u++) h_seg[u] = (int)(u * n);
         if (chunk * n > (size_t)INT32_MAX) return fail("topN: chunk too large");
@@ -1067,15 +1152,15 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
         size_t n_excl_total = 0;
         if (excl_ptr && excl_ix) {
             n_excl_total = (size_t)excl_ptr[n_users];
-            CK(cudaMalloc(&dexp, (n_users + 1) * sizeof(IX)));
-            CK(cudaMalloc(&dexi, std::max<size_t>(n_excl_total, 1) * sizeof(IX)));
+            CK(dmalloc(&dexp, (n_users + 1) * sizeof(IX)));
+            CK(dmalloc(&dexi, std::max<size_t>(n_excl_total, 1) * sizeof(IX)));
             CK(cudaMemcpy(dexp, excl_ptr, (n_users + 1) * sizeof(IX), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(dexi, excl_ix, n_excl_total * sizeof(IX), cudaMemcpyHostToDevice));
         }
         size_t tmp_bytes = 0;
         CK(cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tmp_bytes, sc_in, sc_out, id_in, id_out,
                                                               (int)(chunk * n), (int)chunk, seg, seg + 1));
-        CK(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 1)));
+        CK(dmalloc(&tmp, std::max<size_t>(tmp_bytes, 1)));
         for (size_t u0 = 0; u0 < n_users; u0 += chunk) {
             const size_t m = std::min(chunk, n_users - u0);
             std::vector<long long> hu(m);
@@ -1127,9 +1212,10 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
         return 0;
     };
     int rc = body();
-    cudaFree(dB); cudaFree(dA); cudaFree(dAsel); cudaFree(sc_in); cudaFree(sc_out); cudaFree(id_in);
-    cudaFree(id_out); cudaFree(seg); cudaFree(dusers); cudaFree(dexp); cudaFree(dexi); cudaFree(tmp);
-    cudaFree(d_out_ids); cudaFree(d_out_sc); cudaFree(d_flag); cudaFree(d_neg);
+    if (rc) cudaDeviceSynchronize();
+    dfree(dB); dfree(dA); dfree(dAsel); dfree(sc_in); dfree(sc_out); dfree(id_in);
+    dfree(id_out); dfree(seg); dfree(dusers); dfree(dexp); dfree(dexi); dfree(tmp);
+    dfree(d_out_ids); dfree(d_out_sc); dfree(d_flag); dfree(d_neg);
     // users whose candidate set could not be proven complete: exact scorer, one call for all of them
     if (!rc && !redo.empty()) {
         const size_t R = redo.size();
