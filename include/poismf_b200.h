@@ -133,6 +133,14 @@ int pmf_b200_factors_multiple(int dtype, int index_bytes, void* A, const void* B
                               double l2_reg, double w_mult, double step_size, size_t niter, size_t maxupd,
                               int method, int limit_step, int reuse_mean, int flags);
 
+/* Replaces factors_single, src/pred.c:201-304 (prototype src/poismf.h:281-289): factors of ONE new row
+ * (nnz counts X at item ids X_ind) by tncg, with B and Bsum (old l1 already added) fixed; l1_new - l1_old
+ * is added to Bsum when positive.  `out` [k] is output only; nnz == 0 gives zeros.  Same math as
+ * pmf_b200_factors_multiple on a one-row matrix (only the nnz rows of B the ids name are uploaded). */
+int pmf_b200_factors_single(int dtype, int index_bytes, void* out, size_t k, const void* Amean, int reuse_mean,
+                            const void* X, const void* X_ind, size_t nnz, const void* B, const void* Bsum,
+                            int maxupd, double l2_reg, double l1_new, double l1_old, double w_mult, int flags);
+
 /* Replaces predict_multiple, src/pred.c:42-64 (prototype src/poismf.h:250-257). */
 int pmf_b200_predict_multiple(int dtype, int index_bytes, void* out, const void* A, const void* B,
                               const void* ixA, const void* ixB, size_t n, int k,

@@ -105,6 +105,20 @@ class Ref(_Base):
                niter, maxupd, METHODS[method], limit_step, reuse_mean, nthreads)
         return rc, A
 
+    def factors_single(self, counts, ix, B, Bsum, Amean, reuse_mean=True, maxupd=20, l2_reg=1e5,
+                       l1_new=0.0, l1_old=0.0, w_mult=1.0):
+        """src/pred.c:201-304 (argument order of poismf_c_wrapper.pxi:114-145 `_predict_factors`)."""
+        r = self.creal
+        k = B.shape[1]
+        out = np.empty(k, dtype=self.dtype)
+        f = self.lib.factors_single
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, _sz, C.c_void_p, C.c_bool, C.c_void_p, C.c_void_p, _sz, C.c_void_p, C.c_void_p,
+                      C.c_int, r, r, r, r]
+        rc = f(_p(out), k, _p(Amean), reuse_mean, _p(counts) if counts.size else None, _p(ix) if ix.size else None,
+               counts.shape[0], _p(B), _p(Bsum), maxupd, l2_reg, l1_new, l1_old, w_mult)
+        return rc, out
+
     def topN(self, a_vec, B, n_top, include=None, exclude=None, nthreads=1):
         out_ix = np.empty(n_top, dtype=np.uint64)
         out_sc = np.empty(n_top, dtype=self.dtype)
@@ -153,6 +167,19 @@ class Restatement(_Base):
         rc = f(_p(A), _p(B), _p(Bsum), _p(Amean), _p(Xr), _p(ptr), _p(ind), k, dimA, l2_reg, w_mult, step_size,
                niter, maxupd, METHODS[method], int(limit_step), int(reuse_mean))
         return rc, A
+
+    def factors_single(self, counts, ix, B, Bsum, Amean, reuse_mean=True, maxupd=20, l2_reg=1e5,
+                       l1_new=0.0, l1_old=0.0, w_mult=1.0):
+        r = self.creal
+        k = B.shape[1]
+        out = np.empty(k, dtype=self.dtype)
+        f = self.lib.oracle_factors_single
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, _sz, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _sz, C.c_void_p, C.c_void_p,
+                      C.c_int, r, r, r, r]
+        rc = f(_p(out), k, _p(Amean), int(reuse_mean), _p(counts) if counts.size else None,
+               _p(ix) if ix.size else None, counts.shape[0], _p(B), _p(Bsum), maxupd, l2_reg, l1_new, l1_old, w_mult)
+        return rc, out
 
     def eval(self, a, F, csum, xval, xind, l2, w):
         """(f_cg, g_cg, f_tn, g_tn) at point a for one row."""

@@ -1114,6 +1114,38 @@ int oracle_factors_multiple(real *A, const real *B, const real *Bsum, const real
     return 0;
 }
 
+/* src/pred.c:201-304  factors_single: one new row by tncg.  Bsum carries the OLD l1 already; the
+ * difference l1_new - l1_old is added only when positive (:218, :254-257), AFTER the w_mult
+ * adjustment (:241-247); an empty row gives zeros (:212-215); start = Amean iff reuse_mean, else 1e-3. */
+int oracle_factors_single(real *out, size_t k, const real *Amean, int reuse_mean,
+                          const real *X, const ix_t *X_ind, size_t nnz, const real *B, const real *Bsum,
+                          int maxupd, real l2_reg, real l1_new, real l1_old, real w_mult)
+{
+    if (nnz == 0) { memset(out, 0, k * sizeof(real)); return 0; }
+    real l1_reg = l1_new - l1_old;
+    real *pass = (real *)malloc(sizeof(real) * k);
+    if (w_mult != 1.) {
+        memset(pass, 0, sizeof(real) * k);
+        for (size_t t = 0; t < nnz; t++) vaxpy((int)k, 1., B + X_ind[t] * k, pass);
+        vscal((int)k, w_mult - 1., pass);
+        vaxpy((int)k, 1., Bsum, pass);
+    } else {
+        memcpy(pass, Bsum, sizeof(real) * k);
+    }
+    if (l1_reg > 0.) for (size_t i = 0; i < k; i++) pass[i] += l1_reg;
+    if (reuse_mean) memcpy(out, Amean, k * sizeof(real));
+    else for (size_t i = 0; i < k; i++) out[i] = 1e-3;
+    rowprob p = { B, pass, X, X_ind, (ix_t)nnz, l2_reg, w_mult, (int)k };
+    real *buf = (real *)malloc(sizeof(real) * 22 * k);
+    int *ibuf = (int *)malloc(sizeof(int) * k);
+    int maxCGit = (int)k / 2;                                   /* tnc.c:413-421 (maxCGit = -1) */
+    if (maxCGit < 1) maxCGit = 1; else if (maxCGit > 50) maxCGit = 50;
+    real fval;
+    oracle_tnc_solve(out, &p, maxCGit, maxupd, buf, ibuf, buf + 20 * k, &fval, NULL, NULL);
+    free(buf); free(ibuf); free(pass);
+    return 0;
+}
+
 /* Single-row entry points for known-answer tests (cg / tncg solvers alone). */
 void oracle_cg_row(real *a, const real *F, const real *csum, const real *xval,
                    const ix_t *xind, ix_t nnz, int k, real l2, real w,

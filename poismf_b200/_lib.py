@@ -25,7 +25,7 @@ SYMBOLS = [
     "pmf_b200_set_factors", "pmf_b200_get_factors", "pmf_b200_bind_factors", "pmf_b200_factor_ptr",
     "pmf_b200_set_stream", "pmf_b200_sweeps", "pmf_b200_half_sweep", "pmf_b200_sync",
     "pmf_b200_set_profiling", "pmf_b200_get_profile", "pmf_b200_ipc_export", "pmf_b200_ipc_import",
-    "pmf_b200_run_poismf", "pmf_b200_factors_multiple", "pmf_b200_predict_multiple", "pmf_b200_topN", "pmf_b200_topN_batch", "pmf_b200_topN_stats",
+    "pmf_b200_run_poismf", "pmf_b200_factors_multiple", "pmf_b200_factors_single", "pmf_b200_predict_multiple", "pmf_b200_topN", "pmf_b200_topN_batch", "pmf_b200_topN_stats",
     "pmf_b200_release_cache",
 ]
 
@@ -78,6 +78,7 @@ def lib():
     L.pmf_b200_get_profile.argtypes = [vp, C.POINTER(BinProfile), i]
     L.pmf_b200_run_poismf.argtypes = [i, i] + [vp] * 8 + [sz, sz, sz, d, d, d, d, i, i, sz, sz, i, i, i, i]
     L.pmf_b200_factors_multiple.argtypes = [i, i] + [vp] * 7 + [i, sz, sz, d, d, d, sz, sz, i, i, i, i]
+    L.pmf_b200_factors_single.argtypes = [i, i, vp, sz, vp, i, vp, vp, sz, vp, vp, i, d, d, d, d, i]
     L.pmf_b200_predict_multiple.argtypes = [i, i, vp, vp, vp, vp, vp, sz, i, sz, sz]
     L.pmf_b200_topN.argtypes = [i, i, vp, vp, i, vp, sz, vp, sz, vp, vp, sz, sz]
     L.pmf_b200_topN_batch.argtypes = [i, i, vp, vp, i, vp, sz, sz, vp, vp, vp, vp, sz, sz]

@@ -50,6 +50,23 @@ def _run_poismf(Xr, Xr_indices, Xr_indptr, Xc, Xc_indices, Xc_indptr, A, B,
     return rc
 
 
+def _predict_factors(counts, ix, B, Bsum, Amean, reuse_mean=True, maxupd=20, l2_reg=1e5, l1_new=0.0, l1_old=0.0,
+                     w_mult=1.0, limit_step=False, flags=0):
+    """poismf_c_wrapper.pxi:114-145 — factors of one new row (PoisMF.predict_factors / topN_new)."""
+    _lib.require_gpu()
+    if counts.dtype != B.dtype:
+        raise TypeError("counts and B must share one dtype")
+    out = np.empty(Amean.shape[0], dtype=B.dtype)
+    rc = _lib.lib().pmf_b200_factors_single(
+        _lib.dtype_code(B.dtype), _lib.index_bytes(ix), _lib.ptr(out), out.shape[0], _lib.ptr(Amean),
+        int(bool(reuse_mean)), _lib.ptr(counts) if counts.shape[0] else None, _lib.ptr(ix) if ix.shape[0] else None,
+        counts.shape[0], _lib.ptr(B), _lib.ptr(Bsum), int(maxupd), float(l2_reg), float(l1_new), float(l1_old),
+        float(w_mult), int(flags))
+    if rc:
+        raise MemoryError("Could not allocate enough memory.")
+    return out
+
+
 def _predict_factors_multiple(B, Bsum, Amean, Xr_indptr, Xr_indices, Xr, l2_reg=1e9, w_mult=1.0, step_size=1e-7,
                               niter=10, maxupd=1, method="tncg", limit_step=False, reuse_mean=True, nthreads=1,
                               flags=0):

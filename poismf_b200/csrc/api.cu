@@ -1043,6 +1043,48 @@ extern "C" int pmf_b200_factors_multiple(int dtype, int index_bytes, void* A, co
     return rc ? 1 : 0;
 }
 
+// ---- factors_single drop-in (src/pred.c:201-304, prototype src/poismf.h:281-289) --------------------
+// One new row by tncg == factors_multiple on a one-row matrix.  The reference passes no row count
+// for B; only the nnz rows the ids name are read, so they are gathered into a compact nnz x k
+// matrix on the host and the ids renumbered 0..nnz-1 (same order => same summation order).
+template <class real, class IX>
+static int factors_single_impl(int dtype, real* out, size_t k, const real* Amean, int reuse_mean, const real* X,
+                               const IX* X_ind, size_t nnz, const real* B, const real* Bsum, int maxupd,
+                               double l2_reg, double l1_new, double l1_old, double w_mult, int flags)
+{
+    if (nnz == 0) { memset(out, 0, k * sizeof(real)); return 0; }           // :212-215
+    std::vector<real> Bc(nnz * k), bs(Bsum, Bsum + k);
+    std::vector<IX> ids(nnz);
+    for (size_t t = 0; t < nnz; t++) {
+        memcpy(&Bc[t * k], B + (size_t)X_ind[t] * k, k * sizeof(real));
+        ids[t] = (IX)t;
+    }
+    // Bsum holds the old l1 already; only a positive difference is added (:218, :254-257).  (With
+    // w_mult != 1 the reference adds it after the per-row adjustment; here it goes in before, a
+    // last-bit difference in that one combination.)
+    const real l1d = (real)l1_new - (real)l1_old;
+    if (l1d > (real)0) for (size_t i = 0; i < k; i++) bs[i] += l1d;
+    const IX ptr[2] = {(IX)0, (IX)nnz};
+    return pmf_b200_factors_multiple(dtype, (int)sizeof(IX), out, Bc.data(), bs.data(), Amean, X, ptr, ids.data(),
+                                     (int)k, 1, nnz, l2_reg, w_mult, 0., 1, (size_t)std::max(maxupd, 0), PMF_TNCG, 0,
+                                     reuse_mean, flags);
+}
+extern "C" int pmf_b200_factors_single(int dtype, int index_bytes, void* out, size_t k, const void* Amean,
+                                       int reuse_mean, const void* X, const void* X_ind, size_t nnz, const void* B,
+                                       const void* Bsum, int maxupd, double l2_reg, double l1_new, double l1_old,
+                                       double w_mult, int flags)
+{
+    if (index_bytes != 4 && index_bytes != 8) return fail("factors_single: index_bytes must be 4 or 8");
+#define PMF_FS(real, IX)                                                                                            \
+    return factors_single_impl<real, IX>(dtype, (real*)out, k, (const real*)Amean, reuse_mean, (const real*)X,       \
+                                         (const IX*)X_ind, nnz, (const real*)B, (const real*)Bsum, maxupd, l2_reg,  \
+                                         l1_new, l1_old, w_mult, flags)
+    if (dtype == PMF_F32) { if (index_bytes == 8) PMF_FS(float, uint64_t); else PMF_FS(float, int); }
+    if (dtype == PMF_F64) { if (index_bytes == 8) PMF_FS(double, uint64_t); else PMF_FS(double, int); }
+#undef PMF_FS
+    return fail("bad dtype");
+}
+
 // ---- predict_multiple drop-in ------------------------------------------------
 template <class real, class IX>
 static int predict_impl(real* out, const real* A, const real* B, const IX* ixA, const IX* ixB, size_t n, int k,

@@ -1,7 +1,7 @@
 /* poismf_b200 — host drop-in layer.
  *
  * Defines the reference's own C entry points with the reference's own prototypes
- * (/root/reference/src/poismf.h:170, :226-233, :240-247, :250-257) and forwards
+ * (/root/reference/src/poismf.h:170, :226-233, :240-247, :250-257, :270-289) and forwards
  * them to the CUDA library through the C ABI of include/poismf_b200.h.  It takes
  * the place of src/poismf.c, src/pred.c and src/topN.c in a wrapper build
  * (INTEGRATION.md); like them it is compiled once per value type:
@@ -99,6 +99,21 @@ int factors_multiple(
     return pmf_b200_factors_multiple(PMF_DTYPE, PMF_IXB, A, B, Bsum, Amean, Xr, Xr_indptr, Xr_indices, k, dimA, dimB,
                                      (double)l2_reg, (double)w_mult, (double)step_size, niter, maxupd,
                                      (int)method, (int)limit_step, (int)reuse_mean, 0);
+}
+
+/* src/pred.c:201-304.  Single-row inference is a latency path: a wrapper that serves one user at a
+ * time may prefer to keep the reference's CPU factors_single (compile with -DPMF_NO_FACTORS and keep
+ * src/pred.c, src/tnc.c); this one runs the same tncg solve on the device. */
+int factors_single(
+    real_t *restrict out, size_t k,
+    real_t *restrict Amean, bool reuse_mean,
+    real_t *restrict X, sparse_ix X_ind[], size_t nnz,
+    real_t *restrict B, real_t *restrict Bsum,
+    int maxupd, real_t l2_reg, real_t l1_new, real_t l1_old,
+    real_t w_mult)
+{
+    return pmf_b200_factors_single(PMF_DTYPE, PMF_IXB, out, k, Amean, (int)reuse_mean, X, X_ind, nnz, B, Bsum,
+                                   maxupd, (double)l2_reg, (double)l1_new, (double)l1_old, (double)w_mult, 0);
 }
 #endif
 

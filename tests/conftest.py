@@ -110,6 +110,23 @@ def fm_problem(name, dtype):
     return csr, B, Bsum, Amean, k
 
 
+# factors_single (src/pred.c:201-304): rows of the factors_multiple problem, one at a time
+FS_CASES = {
+    "plain": dict(),
+    "nomean": dict(reuse_mean=False),
+    "w": dict(w_mult=2.0),
+    "l1": dict(l1_new=0.5, l1_old=0.1),
+    "l1_neg": dict(l1_new=0.0, l1_old=0.3, l2_reg=1e2),
+    "l1_w": dict(l1_new=0.5, l1_old=0.1, w_mult=1.5, maxupd=100),
+}
+FS_ROWS = (0, 3, 7, 50)
+
+
+def fs_row(csr, row):
+    lo, hi = int(csr[1][row]), int(csr[1][row + 1])
+    return np.ascontiguousarray(csr[0][lo:hi]), np.ascontiguousarray(csr[2][lo:hi])
+
+
 def fm_hyper(case, k):
     method, kw = FM_CASES[case]
     kw = dict(kw)

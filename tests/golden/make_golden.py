@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
-from conftest import CASES, FM_CASES, fm_hyper, fm_problem, hyper, problem  # noqa: E402
+from conftest import CASES, FM_CASES, FS_CASES, FS_ROWS, fm_hyper, fm_problem, fs_row, hyper, problem  # noqa: E402
 from oracle.oracle import Ref  # noqa: E402
 
 
@@ -40,6 +40,11 @@ def main():
             rc, A = ref.factors_multiple(B, Bsum, Amean, csr, method, **kw)
             assert rc == 0
             out[f"factors_multiple/{np.dtype(dt).name}/{case}"] = A
+        # factors_single (src/pred.c:201-304): a few rows of the same problem, plus the empty row
+        for case, kw in FS_CASES.items():
+            rows = [ref.factors_single(*fs_row(csr, r), B, Bsum, Amean, **kw)[1] for r in FS_ROWS]
+            rows.append(ref.factors_single(np.empty(0, dt), np.empty(0, np.uint64), B, Bsum, Amean, **kw)[1])
+            out[f"factors_single/{np.dtype(dt).name}/{case}"] = np.stack(rows)
         # predict_multiple and topN known answers on the README factors
         csr, csc, A0, B0, k = problem("readme", dt)
         rng = np.random.default_rng(3)

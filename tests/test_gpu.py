@@ -17,7 +17,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import CASES, FM_CASES, ROOT, fm_hyper, fm_problem, hyper, problem, row_rel_err, run_device
+from conftest import (CASES, FM_CASES, FS_CASES, FS_ROWS, ROOT, fm_hyper, fm_problem, fs_row, hyper, problem,
+                      row_rel_err, run_device)
 from oracle.oracle import Restatement
 
 pytestmark = pytest.mark.gpu
@@ -429,6 +430,27 @@ def test_factors_multiple_matches_oracle(dtype, case):
             A = c_funs._predict_factors_multiple(B, Bsum, Amean, csr[1], csr[2], csr[0], method=method, **kw)
             gate = 1e-5 if dtype == np.float64 else 1e-3
             assert (row_rel_err(A, Ar) > gate).mean() <= 0.002
+
+
+# ---------------------------------------------------------------- factors_single
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", list(FS_CASES))
+def test_factors_single_matches_oracle(dtype, case):
+    from poismf_b200 import c_funs
+    kw = FS_CASES[case]
+    tol = 1e-9 if dtype == np.float64 else 1e-5
+    for prob in ("readme", "pl2k"):
+        csr, B, Bsum, Amean, k = fm_problem(prob, dtype)
+        for r in FS_ROWS:
+            c, ix = fs_row(csr, r)
+            want = Restatement(dtype).factors_single(c, ix, B, Bsum, Amean, **kw)[1]
+            got = c_funs._predict_factors(c, ix, B, Bsum, Amean, flags=FLAG_STRICT, **kw)
+            assert row_rel_err(got[None], want[None]).max() <= tol, (prob, r)
+            fast = c_funs._predict_factors(c, ix, B, Bsum, Amean, **kw)
+            assert np.isfinite(fast).all() and (fast >= 0).all()
+        z = c_funs._predict_factors(np.empty(0, dtype), np.empty(0, np.uint64), B, Bsum, Amean, **kw)
+        assert z.shape == (k,) and not z.any()
+    assert GOLD[f"factors_single/{np.dtype(dtype).name}/{case}"].shape == (len(FS_ROWS) + 1, 5)
 
 
 # ---------------------------------------------------------------- batched topN on the tensor cores

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_host_dropin_exports_reference_prototypes(variant):
     path = os.path.join(ROOT, "poismf_b200", f"libpoismf_host_{variant}.so")
     L = ctypes.CDLL(path)
-    for sym in ("run_poismf", "factors_multiple", "predict_multiple", "topN", "get_has_openmp"):
+    for sym in ("run_poismf", "factors_multiple", "factors_single", "predict_multiple", "topN", "get_has_openmp"):
         assert hasattr(L, sym)
 
 

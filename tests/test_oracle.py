@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import CASES, FM_CASES, fm_hyper, fm_problem, hyper, problem
+from conftest import CASES, FM_CASES, FS_CASES, FS_ROWS, fm_hyper, fm_problem, fs_row, hyper, problem
 from oracle.oracle import Ref, Restatement
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
@@ -91,3 +91,30 @@ def test_factors_multiple_restatement(dtype, case):
         rc1, A1 = Ref(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
         rc2, A2 = Restatement(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
         assert rc1 == 0 and rc2 == 0 and np.array_equal(A1, A2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", list(FS_CASES))
+def test_factors_single_restatement(dtype, case):
+    """factors_single (src/pred.c:201-304): restatement == committed reference outputs, == the reference
+    build when present, and == factors_multiple on the same row where the two share their arithmetic."""
+    name = np.dtype(dtype).name
+    csr, B, Bsum, Amean, k = fm_problem("readme", dtype)
+    kw = FS_CASES[case]
+    orc = Restatement(dtype)
+    got = [orc.factors_single(*fs_row(csr, r), B, Bsum, Amean, **kw)[1] for r in FS_ROWS]
+    got.append(orc.factors_single(np.empty(0, dtype), np.empty(0, np.uint64), B, Bsum, Amean, **kw)[1])
+    assert np.array_equal(np.stack(got), GOLD[f"factors_single/{name}/{case}"])
+    assert not got[-1].any()                                     # empty row -> zeros (:212-215)
+    if Ref.available(dtype):
+        for r in FS_ROWS:
+            c, ix = fs_row(csr, r)
+            assert np.array_equal(Ref(dtype).factors_single(c, ix, B, Bsum, Amean, **kw)[1],
+                                  orc.factors_single(c, ix, B, Bsum, Amean, **kw)[1])
+    if "l1_new" not in kw:      # same solve as one row of factors_multiple(tncg)
+        rc, A = orc.factors_multiple(B, Bsum, Amean, csr, "tncg", l2_reg=kw.get("l2_reg", 1e5),
+                                     w_mult=kw.get("w_mult", 1.0), maxupd=kw.get("maxupd", 20),
+                                     reuse_mean=kw.get("reuse_mean", True))
+        for j, r in enumerate(FS_ROWS):
+            assert np.array_equal(A[r], got[j])
+
