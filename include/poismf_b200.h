@@ -133,6 +133,22 @@ int pmf_b200_factors_multiple(int dtype, int index_bytes, void* A, const void* B
                               double l2_reg, double w_mult, double step_size, size_t niter, size_t maxupd,
                               int method, int limit_step, int reuse_mean, int flags);
 
+/* Front-end ingestion on the device (the reference does it on the host with SciPy,
+ * poismf/__init__.py:376-416: coo.tocsr() and coo.tocsc()).  `rows`, `cols` [n_entries] ids at
+ * index_bytes width, `vals` [n_entries] counts, any order, duplicates allowed (they are summed).
+ * pmf_b200_fit_coo = that conversion + run_poismf's sweeps with the matrix never leaving the device;
+ * A [dimA x k] and B [dimB x k] are in/out host arrays.  Returns run_poismf's codes, or 2 when an id
+ * is outside [0, dim).  pmf_b200_coo_to_csr_csc is the conversion alone, into caller arrays sized
+ * n_entries (values, ids) and dim+1 (offsets); *nnz_out = entries stored after summing duplicates. */
+int pmf_b200_fit_coo(int dtype, int index_bytes, void* A, void* B, const void* rows, const void* cols,
+                     const void* vals, size_t n_entries, size_t dimA, size_t dimB, size_t k,
+                     double l2_reg, double l1_reg, double w_mult, double step_size,
+                     int method, int limit_step, size_t numiter, size_t maxupd,
+                     int early_stop, int reuse_prev, int flags);
+int pmf_b200_coo_to_csr_csc(int dtype, int index_bytes, const void* rows, const void* cols, const void* vals,
+                            size_t n_entries, size_t dimA, size_t dimB, void* Xr, void* Xr_indptr,
+                            void* Xr_indices, void* Xc, void* Xc_indptr, void* Xc_indices, size_t* nnz_out);
+
 /* Replaces factors_single, src/pred.c:201-304 (prototype src/poismf.h:281-289): factors of ONE new row
  * (nnz counts X at item ids X_ind) by tncg, with B and Bsum (old l1 already added) fixed; l1_new - l1_old
  * is added to Bsum when positive.  `out` [k] is output only; nnz == 0 gives zeros.  Same math as

@@ -134,3 +134,47 @@ def _topN_batch(A, B, users=None, excl_ptr=None, excl_ix=None, top_n=10, output_
     if rc == 2:
         raise ValueError("topN_batch: invalid arguments")
     return outp_ix, outp_score
+
+
+def _fit_coo(rows, cols, counts, A, B, method="tncg", limit_step=False, l2_reg=1e9, l1_reg=0.0, w_mult=1.0,
+             step_size=1e-7, niter=10, maxupd=1, early_stop=True, reuse_prev=True, flags=0):
+    """PoisMF._process_data + _fit (poismf/__init__.py:376-440) in one call: the COO triplets are turned
+    into CSR and CSC on the device (duplicates summed, ids sorted, as coo.tocsr()/tocsc()) and swept
+    there.  No reference equivalent at the C level (include/poismf_b200.h)."""
+    if counts.shape[0] == 0:
+        raise ValueError("'X' contains no non-zero entries.")
+    if rows.dtype != cols.dtype or A.dtype != B.dtype or A.dtype != counts.dtype:
+        raise TypeError("rows/cols and A/B/counts must share their dtypes")
+    _lib.require_gpu()
+    rc = _lib.lib().pmf_b200_fit_coo(
+        _lib.dtype_code(A.dtype), _lib.index_bytes(rows), _lib.ptr(A), _lib.ptr(B), _lib.ptr(rows), _lib.ptr(cols),
+        _lib.ptr(counts), counts.shape[0], A.shape[0], B.shape[0], A.shape[1],
+        float(l2_reg), float(l1_reg), float(w_mult), float(step_size), _lib.METHODS[method], int(bool(limit_step)),
+        int(niter), int(maxupd), int(bool(early_stop)), int(bool(reuse_prev)), int(flags))
+    if rc == 1:
+        raise MemoryError(_lib.last_error() or "Could not allocate enough memory.")
+    if rc == 2:
+        raise ValueError(_lib.last_error() or "fit_coo: invalid triplets")
+    return rc
+
+
+def _coo_to_csr_csc(rows, cols, counts, dimA, dimB):
+    """coo.tocsr(), coo.tocsc() on the device: ((data, indptr, indices) of CSR, same of CSC)."""
+    _lib.require_gpu()
+    n = counts.shape[0]
+    ixdt = rows.dtype
+    Xr, Xc = np.empty(n, counts.dtype), np.empty(n, counts.dtype)
+    ri, ci = np.empty(n, ixdt), np.empty(n, ixdt)
+    rp, cp = np.empty(dimA + 1, ixdt), np.empty(dimB + 1, ixdt)
+    nnz = ctypes.c_size_t(0)
+    rc = _lib.lib().pmf_b200_coo_to_csr_csc(
+        _lib.dtype_code(counts.dtype), _lib.index_bytes(rows), _lib.ptr(rows), _lib.ptr(cols), _lib.ptr(counts),
+        n, dimA, dimB, _lib.ptr(Xr), _lib.ptr(rp), _lib.ptr(ri), _lib.ptr(Xc), _lib.ptr(cp), _lib.ptr(ci),
+        ctypes.byref(nnz))
+    if rc == 2:
+        raise ValueError(_lib.last_error() or "invalid triplets")
+    if rc:
+        raise MemoryError(_lib.last_error())
+    m = nnz.value
+    return (Xr[:m].copy(), rp, ri[:m].copy()), (Xc[:m].copy(), cp, ci[:m].copy())
+

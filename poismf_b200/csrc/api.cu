@@ -25,6 +25,7 @@
 #include "../../include/poismf_b200.h"
 #include "aux_kernels.cuh"
 #include "devpool.h"
+#include "ingest.cuh"
 #include "kernels.cuh"
 #include "launch.h"
 #include "topn_tc.cuh"
@@ -150,9 +151,13 @@ struct pmf_b200_handle {
     virtual int sweeps(const pmf_b200_params& p) = 0;
     virtual int run_dropin(void* A, void* B, const void* Xr, const void* Xr_indptr, const void* Xr_indices, size_t nnz_r,
                            const void* Xc, const void* Xc_indptr, const void* Xc_indices, size_t nnz_c, int index_bytes,
-                           const pmf_b200_params& p, const std::function<void(const char*)>& lap, bool timing) = 0;
+                           const pmf_b200_params& p, const std::function<void(const char*)>& lap, bool timing,
+                           bool matrix_resident) = 0;
     virtual int factors_multiple(void* A_out, const void* Bsum, const void* Amean, const pmf_b200_params& p,
                                  int reuse_mean) = 0;
+    virtual int ingest_coo(const void* rows, const void* cols, const void* vals, size_t n, int index_bytes) = 0;
+    virtual int export_matrix(int side, void* values, void* indptr, void* indices, int index_bytes) = 0;
+    virtual size_t side_nnz(int side) const = 0;
     virtual int ipc_export(int which, void* out) = 0;
     virtual int ipc_import(int which, const void* handles, int n_ranks, int self_rank) = 0;
     virtual int get_profile(pmf_b200_bin_profile* out, int max_entries) = 0;
@@ -750,6 +755,116 @@ template <class real> struct HandleT : pmf_b200_handle {
         return n;
     }
 
+    // ---- COO triplets -> both orientations, built on the device (ingest.cuh) ---------------------
+    // What coo.tocsr() / coo.tocsc() give the reference (poismf/__init__.py:402-404): duplicates
+    // summed, ids ascending within each row / column.
+    size_t side_nnz(int side) const override { return sides[side].nnz; }
+    template <class IX>
+    int ingest_impl(const IX* rows, const IX* cols, const real* vals, size_t n)
+    {
+        typedef unsigned long long u64;
+        if (n == 0) return fail("fit_coo: no entries");
+        if (n > (size_t)INT32_MAX) return fail("fit_coo: more than 2^31-1 triplets; build CSR/CSC in parts");
+        if (sync_all()) return 1;
+        sides[0].free_all(); sides[1].free_all();
+        IX *d_r = nullptr, *d_c = nullptr;
+        real *v1 = nullptr, *v2 = nullptr;
+        u64 *k1 = nullptr, *k2 = nullptr;
+        int *d_flags = nullptr;        // [0] bad-id flag, [1] number of unique entries
+        void* tmp = nullptr;
+        auto defer = [&](void* q) { deferred.push_back(q); };
+        CK(dmalloc(&d_r, n * sizeof(IX))); defer(d_r);
+        CK(dmalloc(&d_c, n * sizeof(IX))); defer(d_c);
+        CK(dmalloc(&v1, n * sizeof(real))); defer(v1);
+        CK(dmalloc(&v2, n * sizeof(real))); defer(v2);
+        CK(dmalloc(&k1, n * sizeof(u64))); defer(k1);
+        CK(dmalloc(&k2, n * sizeof(u64))); defer(k2);
+        CK(dmalloc(&d_flags, 2 * sizeof(int))); defer(d_flags);
+        CK(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), stream));
+        CK(cudaMemcpyAsync(d_r, rows, n * sizeof(IX), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_c, cols, n * sizeof(IX), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(v1, vals, n * sizeof(real), cudaMemcpyHostToDevice, stream));
+        const int grid = num_sms * 8;
+        coo_keys_kernel<IX><<<grid, 256, 0, stream>>>(d_r, d_c, n, (u64)dimA, (u64)dimB, k1, d_flags);
+        LAUNCHED();
+        auto bits = [](size_t dim) { int b = 1; while (b < 32 && ((size_t)1 << b) < dim) b++; return b; };
+        size_t b_sort1 = 0, b_red = 0, b_sort2 = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, b_sort1, k1, k2, v1, v2, (int)n, 0, 32 + bits(dimA), stream));
+        CK(cub::DeviceReduce::ReduceByKey(nullptr, b_red, k2, k1, v2, v1, d_flags + 1, cub::Sum(), (int)n, stream));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, b_sort2, k2, k1, v1, v2, (int)n, 0, 32 + bits(dimB), stream));
+        const size_t tmp_bytes = std::max(std::max(b_sort1, b_red), std::max<size_t>(b_sort2, 16));
+        CK(dmalloc(&tmp, tmp_bytes)); defer(tmp);
+        size_t tb = tmp_bytes;
+        // (row, col)-sorted, stable: duplicates stay in input order
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tb, k1, k2, v1, v2, (int)n, 0, 32 + bits(dimA), stream));
+        LAUNCHED();
+        tb = tmp_bytes;
+        CK(cub::DeviceReduce::ReduceByKey(tmp, tb, k2, k1, v2, v1, d_flags + 1, cub::Sum(), (int)n, stream));
+        LAUNCHED();
+        int h_flags[2] = {0, 0};
+        CK(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (h_flags[0]) { sync_all(); g_err = "fit_coo: an id is outside [0, dim)"; return 2; }
+        const size_t nnz = (size_t)h_flags[1];
+        // unique (row, col) keys are in k1[0..nnz), their summed values in v1[0..nnz)
+        auto build = [&](Side<real>& S, const u64* keys, const real* values, size_t nmajor) -> int {
+            S.nnz = nnz; S.row_begin = 0; S.n_rows = nmajor;
+            CK(dmalloc(&S.xv, std::max<size_t>(nnz, 1) * sizeof(real)));
+            CK(dmalloc(&S.ind, std::max<size_t>(nnz, 1) * sizeof(int)));
+            CK(dmalloc(&S.ptr, (nmajor + 1) * sizeof(long long)));
+            CK(cudaMemcpyAsync(S.xv, values, nnz * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+            minor_ids_kernel<<<grid, 256, 0, stream>>>(keys, nnz, S.ind);
+            LAUNCHED();
+            key_offsets_kernel<<<grid, 256, 0, stream>>>(keys, nnz, nmajor, S.ptr);
+            LAUNCHED();
+            CK(cudaGetLastError());
+            S.h_ptr.resize(nmajor + 1);
+            CK(cudaMemcpyAsync(S.h_ptr.data(), S.ptr, (nmajor + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+            return 0;
+        };
+        if (build(sides[PMF_SIDE_CSR], k1, v1, dimA)) return 1;
+        swap_keys_kernel<<<grid, 256, 0, stream>>>(k1, nnz, k2);
+        LAUNCHED();
+        tb = tmp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tb, k2, k1, v1, v2, (int)nnz, 0, 32 + bits(dimB), stream));
+        LAUNCHED();
+        if (build(sides[PMF_SIDE_CSC], k1, v2, dimB)) return 1;
+        return sync_all();
+    }
+    int ingest_coo(const void* rows, const void* cols, const void* vals, size_t n, int index_bytes) override
+    {
+        CK(cudaSetDevice(device));
+        if (index_bytes == 8) return ingest_impl<uint64_t>((const uint64_t*)rows, (const uint64_t*)cols, (const real*)vals, n);
+        if (index_bytes == 4) return ingest_impl<int>((const int*)rows, (const int*)cols, (const real*)vals, n);
+        return fail("fit_coo: index_bytes must be 4 or 8");
+    }
+    // device CSR / CSC back to host arrays at the caller's index width (tests, and callers that want
+    // the conversion alone)
+    int export_matrix(int side, void* values, void* indptr, void* indices, int index_bytes) override
+    {
+        CK(cudaSetDevice(device));
+        Side<real>& S = sides[side];
+        if (!S.ptr) return fail("export_matrix: side %d not set", side);
+        if (index_bytes != 4 && index_bytes != 8) return fail("export_matrix: index_bytes must be 4 or 8");
+        const int grid = num_sms * 8;
+        CK(cudaMemcpyAsync(values, S.xv, S.nnz * sizeof(real), cudaMemcpyDeviceToHost, stream));
+        if (index_bytes == 4) {
+            CK(cudaMemcpyAsync(indices, S.ind, S.nnz * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            int* p32 = (int*)indptr;
+            for (size_t i = 0; i <= S.n_rows; i++) p32[i] = (int)S.h_ptr[i];
+        } else {
+            uint64_t* w = nullptr;
+            CK(dmalloc(&w, std::max<size_t>(S.nnz, 1) * sizeof(uint64_t)));
+            deferred.push_back(w);
+            widen_ids_kernel<uint64_t><<<grid, 256, 0, stream>>>(S.ind, S.nnz, w);
+            LAUNCHED();
+            CK(cudaMemcpyAsync(indices, w, S.nnz * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+            uint64_t* p64 = (uint64_t*)indptr;
+            for (size_t i = 0; i <= S.n_rows; i++) p64[i] = (uint64_t)S.h_ptr[i];
+        }
+        return sync_all();
+    }
+
     // ---- factors_multiple (src/pred.c:66-199): rows of A for new data, B and Bsum fixed ---------
     // The handle holds the new rows' CSR on the CSR side and B; A (dimA rows) is produced here.
     int factors_multiple(void* A_out, const void* Bsum_v, const void* Amean_v, const pmf_b200_params& p,
@@ -836,20 +951,25 @@ template <class real> struct HandleT : pmf_b200_handle {
     //   copy_stream:                      | CSR up, plan ------------^ | (last sweep) B down
     int run_dropin(void* Ah, void* Bh, const void* Xr, const void* Xr_indptr, const void* Xr_indices, size_t nnz_r,
                    const void* Xc, const void* Xc_indptr, const void* Xc_indices, size_t nnz_c, int index_bytes,
-                   const pmf_b200_params& p, const std::function<void(const char*)>& lap, bool timing) override
+                   const pmf_b200_params& p, const std::function<void(const char*)>& lap, bool timing,
+                   bool matrix_resident) override
     {
+        // matrix_resident: both orientations are already on the device from an earlier call with the
+        // same arrays (POISMF_B200_CACHE_X); only the factors travel
         CK(cudaSetDevice(device));
         const bool strict = (p.flags & PMF_FLAG_STRICT) != 0;
         if (copy_in(A, Ah, dimA, stream)) return 1;
         if (copy_in(B, Bh, dimB, stream)) return 1;
-        if (upload_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, nnz_c, index_bytes, 0, dimB, stream)) return 1;
+        if (!matrix_resident &&
+            upload_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, nnz_c, index_bytes, 0, dimB, stream)) return 1;
         if (plan(sides[PMF_SIDE_CSC], p.method, strict, stream)) return 1;
         if (timing) { if (sync_all()) return 1; lap("up A,B,CSC+plan"); }
         bool csr_up = false, b_down = false;
         SweepHooks hk;
         hk.before_first_A = [&]() -> int {
             csr_up = true;
-            if (upload_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, nnz_r, index_bytes, 0, dimA, copy_stream)) return 1;
+            if (!matrix_resident &&
+                upload_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, nnz_r, index_bytes, 0, dimA, copy_stream)) return 1;
             if (plan(sides[PMF_SIDE_CSR], p.method, strict, copy_stream)) return 1;
             CK(cudaEventRecord(ev_copy, copy_stream));
             CK(cudaStreamWaitEvent(stream, ev_copy, 0));
@@ -934,12 +1054,61 @@ extern "C" int pmf_b200_get_profile(pmf_b200_handle* h, pmf_b200_bin_profile* ou
 {
     return h->get_profile(out, max_entries);
 }
-extern "C" size_t pmf_b200_release_cache(void) { return DevPool::get().release(-1); }
+static void drop_matrix_cache();
+extern "C" size_t pmf_b200_release_cache(void)
+{
+    drop_matrix_cache();
+    return DevPool::get().release(-1);
+}
 extern "C" int pmf_b200_sync(pmf_b200_handle* h)
 {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// ---- matrix cache of the stateless drop-in call (opt-in, POISMF_B200_CACHE_X=1) ------------------------
+// Key: device, types, shapes, the six host pointers and a fingerprint of each array (all of indptr,
+// 4096 evenly spaced 8-byte words of values / indices plus their last word).  The fingerprint detects
+// ordinary in-place edits, not adversarial ones: that is why the cache is opt-in.
+struct XKey {
+    int device = -1, dtype = -1, index_bytes = 0;
+    size_t dimA = 0, dimB = 0, k = 0, nnz_r = 0, nnz_c = 0;
+    const void* ptr[6] = {};
+    uint64_t fp[6] = {};
+    bool operator==(const XKey& o) const
+    {
+        if (device != o.device || dtype != o.dtype || index_bytes != o.index_bytes || dimA != o.dimA ||
+            dimB != o.dimB || k != o.k || nnz_r != o.nnz_r || nnz_c != o.nnz_c) return false;
+        for (int i = 0; i < 6; i++) if (ptr[i] != o.ptr[i] || fp[i] != o.fp[i]) return false;
+        return true;
+    }
+};
+static uint64_t fingerprint(const void* p, size_t bytes, bool full)
+{
+    uint64_t hsh = 0x243f6a8885a308d3ULL ^ bytes;
+    auto mix = [&](uint64_t v) { hsh ^= v + 0x9e3779b97f4a7c15ULL + (hsh << 6) + (hsh >> 2); };
+    const size_t words = bytes / 8;
+    const unsigned char* b = (const unsigned char*)p;
+    auto word = [&](size_t i) { uint64_t v; memcpy(&v, b + i * 8, 8); return v; };
+    if (full || words <= 8192) {
+        for (size_t i = 0; i < words; i++) mix(word(i));
+    } else {
+        const size_t stride = words / 4096;
+        for (size_t i = 0; i < words; i += stride) mix(word(i));
+        mix(word(words - 1));
+    }
+    for (size_t i = words * 8; i < bytes; i++) mix(b[i]);
+    return hsh;
+}
+static std::mutex g_xcache_mutex;
+static pmf_b200_handle* g_xcache_handle = nullptr;
+static XKey g_xcache_key;
+static void drop_matrix_cache()
+{
+    std::lock_guard<std::mutex> g(g_xcache_mutex);
+    if (g_xcache_handle) pmf_b200_destroy(g_xcache_handle);
+    g_xcache_handle = nullptr;
 }
 
 // ---- run_poismf drop-in ------------------------------------------------------
@@ -985,21 +1154,46 @@ extern "C" int pmf_b200_run_poismf(int dtype, int index_bytes,
         if (!timing) return;
         t1 = now(); fprintf(stderr, "poismf_b200 timing: %-14s %8.2f ms\n", what, t1 - t0); t0 = t1;
     };
-    pmf_b200_handle* h = pmf_b200_create(dtype, dimA, dimB, k, env_device());
-    lap("create");
-    if (!h) rc = 1;
     const size_t isz = (size_t)index_bytes;
     auto span = [&](const void* ptr, size_t n) -> size_t {
         return isz == 8 ? (size_t)(((const uint64_t*)ptr)[n] - ((const uint64_t*)ptr)[0])
                         : (size_t)(((const int*)ptr)[n] - ((const int*)ptr)[0]);
     };
+    const size_t nnz_r = span(Xr_indptr, dimA), nnz_c = span(Xc_indptr, dimB);
+    const size_t rsz = dtype == PMF_F32 ? 4 : 8;
+    // POISMF_B200_CACHE_X: keep the uploaded matrix (both orientations + row plan) for the next call
+    // with the same arrays (repeated fits on one dataset)
+    XKey key;
+    const bool use_cache = getenv("POISMF_B200_CACHE_X") != nullptr && atoi(getenv("POISMF_B200_CACHE_X")) != 0;
+    pmf_b200_handle* h = nullptr;
+    bool resident = false;
+    if (use_cache) {
+        key.device = env_device(); key.dtype = dtype; key.index_bytes = index_bytes;
+        key.dimA = dimA; key.dimB = dimB; key.k = k; key.nnz_r = nnz_r; key.nnz_c = nnz_c;
+        const void* ptrs[6] = {Xr, Xr_indptr, Xr_indices, Xc, Xc_indptr, Xc_indices};
+        const size_t bytes[6] = {nnz_r * rsz, (dimA + 1) * isz, nnz_r * isz, nnz_c * rsz, (dimB + 1) * isz, nnz_c * isz};
+        for (int i = 0; i < 6; i++) { key.ptr[i] = ptrs[i]; key.fp[i] = fingerprint(ptrs[i], bytes[i], i == 1 || i == 4); }
+        std::lock_guard<std::mutex> g(g_xcache_mutex);
+        if (g_xcache_handle && g_xcache_key == key) { h = g_xcache_handle; resident = true; }
+        else if (g_xcache_handle) pmf_b200_destroy(g_xcache_handle);
+        g_xcache_handle = nullptr;       // taken (or dropped); put back after the fit
+    }
+    if (!h) h = pmf_b200_create(dtype, dimA, dimB, k, env_device());
+    lap(resident ? "reuse handle" : "create");
+    if (!h) rc = 1;
     if (!rc) {
         pmf_b200_params p;
         p.l2_reg = l2_reg; p.l1_reg = l1_reg; p.w_mult = w_mult; p.step_size = step_size;
         p.method = method; p.limit_step = limit_step; p.numiter = numiter; p.maxupd = maxupd;
         p.early_stop = early_stop; p.reuse_prev = reuse_prev; p.flags = env_flags(flags);
-        rc = h->run_dropin(A, B, Xr, Xr_indptr, Xr_indices, span(Xr_indptr, dimA), Xc, Xc_indptr, Xc_indices,
-                           span(Xc_indptr, dimB), index_bytes, p, lap, timing);
+        rc = h->run_dropin(A, B, Xr, Xr_indptr, Xr_indices, nnz_r, Xc, Xc_indptr, Xc_indices, nnz_c, index_bytes, p,
+                           lap, timing, resident);
+    }
+    if (h && use_cache && rc != 1) {
+        std::lock_guard<std::mutex> g(g_xcache_mutex);
+        if (g_xcache_handle) pmf_b200_destroy(g_xcache_handle);
+        g_xcache_handle = h; g_xcache_key = key;
+        h = nullptr;
     }
     if (h) pmf_b200_destroy(h);
     lap("destroy");
@@ -1041,6 +1235,45 @@ extern "C" int pmf_b200_factors_multiple(int dtype, int index_bytes, void* A, co
     pmf_b200_destroy(h);
     if (rc) fprintf(stderr, "Error: out of memory.\n");
     return rc ? 1 : 0;
+}
+
+// ---- fit straight from COO triplets (front-end ingestion on the device) ------------
+// = PoisMF._process_data + _fit (poismf/__init__.py:376-440) without the host-side tocsr()/tocsc().
+extern "C" int pmf_b200_fit_coo(int dtype, int index_bytes, void* A, void* B, const void* rows, const void* cols,
+                                const void* vals, size_t n_entries, size_t dimA, size_t dimB, size_t k,
+                                double l2_reg, double l1_reg, double w_mult, double step_size,
+                                int method, int limit_step, size_t numiter, size_t maxupd,
+                                int early_stop, int reuse_prev, int flags)
+{
+    pmf_b200_handle* h = pmf_b200_create(dtype, dimA, dimB, k, env_device());
+    if (!h) return 1;
+    int rc = h->ingest_coo(rows, cols, vals, n_entries, index_bytes);
+    if (!rc) rc = h->set_factors(A, B);
+    if (!rc) {
+        pmf_b200_params p;
+        p.l2_reg = l2_reg; p.l1_reg = l1_reg; p.w_mult = w_mult; p.step_size = step_size;
+        p.method = method; p.limit_step = limit_step; p.numiter = numiter; p.maxupd = maxupd;
+        p.early_stop = early_stop; p.reuse_prev = reuse_prev; p.flags = env_flags(flags);
+        rc = h->sweeps(p);
+        if (rc != 1 && h->get_factors(A, B)) rc = 1;
+    }
+    pmf_b200_destroy(h);
+    return rc;
+}
+// The conversion alone: CSR and CSC of the triplets into caller arrays sized for n_entries values /
+// ids and dim+1 offsets; *nnz_out = stored entries after summing duplicates.
+extern "C" int pmf_b200_coo_to_csr_csc(int dtype, int index_bytes, const void* rows, const void* cols, const void* vals,
+                                       size_t n_entries, size_t dimA, size_t dimB, void* Xr, void* Xr_indptr,
+                                       void* Xr_indices, void* Xc, void* Xc_indptr, void* Xc_indices, size_t* nnz_out)
+{
+    pmf_b200_handle* h = pmf_b200_create(dtype, dimA, dimB, 1, env_device());
+    if (!h) return 1;
+    int rc = h->ingest_coo(rows, cols, vals, n_entries, index_bytes);
+    if (!rc) rc = h->export_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, index_bytes);
+    if (!rc) rc = h->export_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, index_bytes);
+    if (!rc && nnz_out) *nnz_out = h->side_nnz(PMF_SIDE_CSR);
+    pmf_b200_destroy(h);
+    return rc;
 }
 
 // ---- factors_single drop-in (src/pred.c:201-304, prototype src/poismf.h:281-289) --------------------

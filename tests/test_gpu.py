@@ -432,6 +432,93 @@ def test_factors_multiple_matches_oracle(dtype, case):
             assert (row_rel_err(A, Ar) > gate).mean() <= 0.002
 
 
+# ---------------------------------------------------------------- COO ingestion
+def _coo_case(dtype, ixdt, seed=11, n=40000, dimA=700, dimB=300):
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, dimA, n).astype(ixdt)
+    cols = (rng.zipf(1.6, n) % dimB).astype(ixdt)                 # heavy columns, many duplicates
+    vals = (1 + rng.geometric(0.5, n)).astype(dtype)
+    rows[rows == 13] = 14                                          # an empty row; column dimB-1 stays rare
+    return rows, cols, vals, dimA, dimB
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ixdt", [np.uint64, np.int32])
+def test_coo_ingestion_matches_scipy(dtype, ixdt):
+    """coo.tocsr() / coo.tocsc() (poismf/__init__.py:402-404) on the device: same offsets, ids and
+    summed counts, bit for bit."""
+    from scipy.sparse import coo_matrix
+    from poismf_b200 import c_funs
+    rows, cols, vals, dimA, dimB = _coo_case(dtype, ixdt)
+    coo = coo_matrix((vals, (rows.astype(np.int64), cols.astype(np.int64))), shape=(dimA, dimB))
+    for got, want in zip(c_funs._coo_to_csr_csc(rows, cols, vals, dimA, dimB), (coo.tocsr(), coo.tocsc())):
+        assert want.has_sorted_indices
+        assert np.array_equal(got[1].astype(np.int64), want.indptr.astype(np.int64))
+        assert np.array_equal(got[2].astype(np.int64), want.indices.astype(np.int64))
+        assert np.array_equal(got[0], want.data.astype(dtype))
+    bad = rows.copy(); bad[5] = dimA
+    with pytest.raises(ValueError):
+        c_funs._coo_to_csr_csc(bad, cols, vals, dimA, dimB)
+
+
+@pytest.mark.parametrize("case", ["pg", "cg", "tncg"])
+def test_fit_from_coo_equals_fit_from_scipy_csr_csc(case):
+    from scipy.sparse import coo_matrix
+    from poismf_b200 import c_funs
+    from poismf_b200.synth import init_factors
+    dtype, k = np.float32, 16
+    rows, cols, vals, dimA, dimB = _coo_case(dtype, np.uint64, seed=12)
+    coo = coo_matrix((vals, (rows.astype(np.int64), cols.astype(np.int64))), shape=(dimA, dimB))
+    csr, csc = coo.tocsr(), coo.tocsc()
+    trip = lambda m: (np.ascontiguousarray(m.data, dtype=dtype), np.ascontiguousarray(m.indptr, dtype=np.uint64),
+                      np.ascontiguousarray(m.indices, dtype=np.uint64))
+    A0, B0 = init_factors(dimA, dimB, k, dtype=dtype)
+    method, kw = hyper(case, k)
+    A, B = A0.copy(), B0.copy()
+    assert run_device(trip(csr), trip(csc), A, B, method, kw) == 0
+    A2, B2 = A0.copy(), B0.copy()
+    rc = c_funs._fit_coo(rows, cols, vals, A2, B2, method=method, limit_step=kw.get("limit_step", False),
+                         l2_reg=kw["l2_reg"], step_size=kw.get("step_size", 1e-7), niter=kw["numiter"],
+                         maxupd=kw["maxupd"], early_stop=False, reuse_prev=False)
+    assert rc == 0 and np.array_equal(A, A2) and np.array_equal(B, B2)
+    assert not A2[13].any()                                        # the empty row is zeroed (Q6)
+
+
+# ---------------------------------------------------------------- matrix cache (SURVEY §8f rank 3)
+def test_matrix_cache_between_dropin_calls(monkeypatch):
+    """POISMF_B200_CACHE_X=1 keeps the uploaded matrix for the next run_poismf on the same arrays:
+    results are those of the uncached call, a changed method re-plans, and in-place edits of the
+    arrays are noticed."""
+    from poismf_b200 import _lib
+    dtype = np.float32
+    csr, csc, A0, B0, k = problem("pl6k", dtype)
+
+    def fit(case, flags=0):
+        method, kw = hyper(case, k)
+        A, B = A0.copy(), B0.copy()
+        assert run_device(csr, csc, A, B, method, kw, flags=flags) == 0
+        return A, B
+
+    want = {c: fit(c) for c in ("cg", "pg", "tncg")}
+    monkeypatch.setenv("POISMF_B200_CACHE_X", "1")
+    for c in ("cg", "cg", "pg", "tncg", "cg"):           # first call fills the cache, the others hit it
+        A, B = fit(c)
+        assert np.array_equal(A, want[c][0]) and np.array_equal(B, want[c][1]), c
+    A, B = fit("pg", flags=FLAG_STRICT)                   # strict numerics re-plan on the cached matrix
+    monkeypatch.delenv("POISMF_B200_CACHE_X")
+    As, Bs = fit("pg", flags=FLAG_STRICT)
+    assert np.array_equal(A, As) and np.array_equal(B, Bs)
+    monkeypatch.setenv("POISMF_B200_CACHE_X", "1")
+    fit("cg")
+    csr[0][:] *= 2; csc[0][:] *= 2                        # same pointers, new contents
+    A, B = fit("cg")
+    monkeypatch.delenv("POISMF_B200_CACHE_X")
+    A2, B2 = fit("cg")
+    assert np.array_equal(A, A2) and np.array_equal(B, B2)
+    assert not np.array_equal(A, want["cg"][0])
+    _lib.lib().pmf_b200_release_cache()
+
+
 # ---------------------------------------------------------------- factors_single (SURVEY §8f rank 2)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("case", list(FS_CASES))
