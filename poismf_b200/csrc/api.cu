@@ -26,6 +26,7 @@
 #include "aux_kernels.cuh"
 #include "devpool.h"
 #include "ingest.cuh"
+#include "staged_copy.h"
 #include "kernels.cuh"
 #include "launch.h"
 #include "topn_tc.cuh"
@@ -267,11 +268,11 @@ template <class real> struct HandleT : pmf_b200_handle {
         CK(dmalloc(&S.xv, std::max<size_t>(nnz, 1) * sizeof(real)));
         CK(dmalloc(&S.ind, std::max<size_t>(nnz, 1) * sizeof(int)));
         CK(dmalloc(&S.ptr, (n_rows + 1) * sizeof(long long)));
-        CK(cudaMemcpyAsync(S.xv, values, nnz * sizeof(real), cudaMemcpyHostToDevice, st));
+        CK(Stager::get().h2d(S.xv, values, nnz * sizeof(real), st));
         CK(cudaMemcpyAsync(S.ptr, S.h_ptr.data(), (n_rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
         // indices: upload at host width, narrow to int32 on the device
         if (sizeof(IX) == sizeof(int)) {
-            CK(cudaMemcpyAsync(S.ind, indices, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+            CK(Stager::get().h2d(S.ind, indices, nnz * sizeof(int), st));
         } else {
             IX* tmp = nullptr;
             const size_t chunk = (size_t)1 << 27;   // bounded staging buffer (1 GiB of 8-byte ids)
@@ -279,7 +280,7 @@ template <class real> struct HandleT : pmf_b200_handle {
             deferred.push_back(tmp);
             for (size_t off = 0; off < nnz; off += chunk) {
                 const size_t m = std::min(chunk, nnz - off);
-                CK(cudaMemcpyAsync(tmp, indices + off, m * sizeof(IX), cudaMemcpyHostToDevice, st));
+                CK(Stager::get().h2d(tmp, indices + off, m * sizeof(IX), st));
                 narrow_indices_kernel<IX><<<num_sms * 8, 256, 0, st>>>(tmp, S.ind + off, m);
                 LAUNCHED();
                 CK(cudaGetLastError());
@@ -316,11 +317,11 @@ template <class real> struct HandleT : pmf_b200_handle {
     // (a pitched cudaMemcpy2D of 200-byte rows is ~10x slower over PCIe)
     int copy_in(real* dev, const void* host, size_t n, cudaStream_t st)
     {
-        if (ldf == k) { CK(cudaMemcpyAsync(dev, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, st)); return 0; }
+        if (ldf == k) { CK(Stager::get().h2d(dev, host, n * (size_t)k * sizeof(real), st)); return 0; }
         real* tmp = nullptr;
         CK(dmalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
         deferred.push_back(tmp);
-        CK(cudaMemcpyAsync(tmp, host, n * (size_t)k * sizeof(real), cudaMemcpyHostToDevice, st));
+        CK(Stager::get().h2d(tmp, host, n * (size_t)k * sizeof(real), st));
         pad_rows_kernel<real><<<num_sms * 8, 256, 0, st>>>(tmp, dev, n, k, ldf);
         LAUNCHED();
         CK(cudaGetLastError());
@@ -328,14 +329,14 @@ template <class real> struct HandleT : pmf_b200_handle {
     }
     int copy_out(void* host, const real* dev, size_t n, cudaStream_t st)
     {
-        if (ldf == k) { CK(cudaMemcpyAsync(host, dev, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, st)); return 0; }
+        if (ldf == k) { CK(Stager::get().d2h(host, dev, n * (size_t)k * sizeof(real), st)); return 0; }
         real* tmp = nullptr;
         CK(dmalloc(&tmp, std::max<size_t>(n * (size_t)k, 1) * sizeof(real)));
         deferred.push_back(tmp);
         unpad_rows_kernel<real><<<num_sms * 8, 256, 0, st>>>(dev, tmp, n, k, ldf);
         LAUNCHED();
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(host, tmp, n * (size_t)k * sizeof(real), cudaMemcpyDeviceToHost, st));
+        CK(Stager::get().d2h(host, tmp, n * (size_t)k * sizeof(real), st));
         return 0;
     }
     int set_factors(const void* Ah, const void* Bh) override
@@ -781,9 +782,9 @@ template <class real> struct HandleT : pmf_b200_handle {
         CK(dmalloc(&k2, n * sizeof(u64))); defer(k2);
         CK(dmalloc(&d_flags, 2 * sizeof(int))); defer(d_flags);
         CK(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), stream));
-        CK(cudaMemcpyAsync(d_r, rows, n * sizeof(IX), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_c, cols, n * sizeof(IX), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(v1, vals, n * sizeof(real), cudaMemcpyHostToDevice, stream));
+        CK(Stager::get().h2d(d_r, rows, n * sizeof(IX), stream));
+        CK(Stager::get().h2d(d_c, cols, n * sizeof(IX), stream));
+        CK(Stager::get().h2d(v1, vals, n * sizeof(real), stream));
         const int grid = num_sms * 8;
         coo_keys_kernel<IX><<<grid, 256, 0, stream>>>(d_r, d_c, n, (u64)dimA, (u64)dimB, k1, d_flags);
         LAUNCHED();
@@ -910,9 +911,11 @@ template <class real> struct HandleT : pmf_b200_handle {
     // ---- numiter alternating sweeps (src/poismf.c:506-608) -------------------------
     // hooks of the pipelined drop-in call: `before_first_A` runs on the host right after the first B
     // half-sweep has been enqueued (it uploads the CSR orientation behind it), `after_last_B` right
-    // after the last one (it starts B's download while A's rows are still being solved)
+    // after the last one (it marks B as final), `after_last_A` once the last A half-sweep has been
+    // enqueued (it downloads B while A's rows are still being solved; a pageable destination makes
+    // that copy block the host, hence only after the enqueue)
     struct SweepHooks {
-        std::function<int()> before_first_A, after_last_B;
+        std::function<int()> before_first_A, after_last_B, after_last_A;
     };
     int sweeps(const pmf_b200_params& p) override { return sweeps_ex(p, nullptr); }
     int sweeps_ex(const pmf_b200_params& p, SweepHooks* hk)
@@ -941,6 +944,7 @@ template <class real> struct HandleT : pmf_b200_handle {
                 if (p.method == PMF_TNCG && p.early_stop)
                     stopA = ((double)unch / (double)dimA) >= .95;
             }
+            if (hk && it + 1 == p.numiter && hk->after_last_A()) return 1;
             if (stopA && stopB) break;                                                        // :606
         }
         return 0;
@@ -976,17 +980,23 @@ template <class real> struct HandleT : pmf_b200_handle {
             if (timing) { cudaStreamSynchronize(copy_stream); lap("up CSR+plan"); cudaStreamSynchronize(stream); lap("B half-sweep"); }
             return 0;
         };
+        bool b_final = false;
         hk.after_last_B = [&]() -> int {
-            b_down = true;
+            b_final = true;
             CK(cudaEventRecord(ev_main, stream));
-            CK(cudaStreamWaitEvent(copy_stream, ev_main, 0));
+            return 0;
+        };
+        hk.after_last_A = [&]() -> int {
+            b_down = true;
+            if (b_final) CK(cudaStreamWaitEvent(copy_stream, ev_main, 0));
+            else { CK(cudaEventRecord(ev_main, stream)); CK(cudaStreamWaitEvent(copy_stream, ev_main, 0)); }
             return copy_out(Bh, B, dimB, copy_stream);
         };
         int rc = sweeps_ex(p, &hk);
         if (rc == 1) { sync_all(); return 1; }
         if (timing) { cudaStreamSynchronize(stream); lap("rest of sweeps"); }
         // interrupted fits (rc 2) still return the factors computed so far
-        if (!b_down && hk.after_last_B()) rc = 1;
+        if (!b_down && hk.after_last_A()) rc = 1;
         if (copy_out(Ah, A, dimA, stream)) rc = 1;
         if (sync_all()) rc = 1;
         if (timing) lap("download");
