@@ -1418,12 +1418,106 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             CK(cudaMemcpy(&neg, d_neg, sizeof(int), cudaMemcpyDeviceToHost));
             if (neg) use_tc = false;      // the TF32 error bound below assumes non-negative factors
         }
+        const size_t ntiles = (n + tc::TN - 1) / tc::TN, ngroups = (n + tc::GROUP - 1) / tc::GROUP;
+        if (use_tc && ngroups >= (size_t)2 * M_cand && !getenv("POISMF_B200_TOPN_SORT")) {
+            // ---- fused select (topn_tc.cuh): no score matrix; two passes over the tensor-core tiles ----
+            const size_t words = ntiles * 4;     // exclusion bitmap: 128 bits per tile and user
+            const bool have_excl = excl_ptr && excl_ix;
+            const size_t per_user = ngroups * 4 + (have_excl ? words * 4 : 0) + (size_t)tc::CAND_CAP * 8 +
+                                    (size_t)tc::CAND_TOP * 8 + pitch + n_top * 12 + 64;
+            size_t fchunk = std::max<size_t>(1, std::min<size_t>(n_users, ((size_t)1 << 30) / per_user));
+            fchunk = std::min<size_t>(fchunk, 32768);
+            float *gmax = nullptr, *tau = nullptr, *cand_sc = nullptr, *top_sc = nullptr;
+            int *cand_id = nullptr, *cand_cnt = nullptr, *top_id = nullptr, *d_ovf = nullptr;
+            uint32_t* bits = nullptr;
+            std::vector<void*> mine;
+            auto take = [&](void* q) { mine.push_back(q); };
+            auto fused = [&]() -> int {
+                CK(dmalloc(&dAsel, fchunk * pitch));
+                CK(dmalloc(&dusers, fchunk * sizeof(long long)));
+                CK(dmalloc(&gmax, fchunk * ngroups * sizeof(float))); take(gmax);
+                CK(dmalloc(&tau, fchunk * sizeof(float))); take(tau);
+                CK(dmalloc(&cand_sc, fchunk * tc::CAND_CAP * sizeof(float))); take(cand_sc);
+                CK(dmalloc(&cand_id, fchunk * tc::CAND_CAP * sizeof(int))); take(cand_id);
+                CK(dmalloc(&cand_cnt, fchunk * sizeof(int))); take(cand_cnt);
+                CK(dmalloc(&top_sc, fchunk * tc::CAND_TOP * sizeof(float))); take(top_sc);
+                CK(dmalloc(&top_id, fchunk * tc::CAND_TOP * sizeof(int))); take(top_id);
+                CK(dmalloc(&d_ovf, fchunk * sizeof(int))); take(d_ovf);
+                CK(dmalloc(&d_out_ids, fchunk * n_top * sizeof(long long)));
+                CK(dmalloc(&d_out_sc, fchunk * n_top * sizeof(float)));
+                CK(dmalloc(&d_flag, fchunk * sizeof(int)));
+                if (have_excl) {
+                    const size_t n_excl_total = (size_t)excl_ptr[n_users];
+                    CK(dmalloc(&bits, fchunk * words * sizeof(uint32_t))); take(bits);
+                    CK(dmalloc(&dexp, (n_users + 1) * sizeof(IX)));
+                    CK(dmalloc(&dexi, std::max<size_t>(n_excl_total, 1) * sizeof(IX)));
+                    CK(cudaMemcpy(dexp, excl_ptr, (n_users + 1) * sizeof(IX), cudaMemcpyHostToDevice));
+                    CK(cudaMemcpy(dexi, excl_ix, n_excl_total * sizeof(IX), cudaMemcpyHostToDevice));
+                }
+                CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel<tc::MODE_GROUPMAX>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kpad * 1024));
+                CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel<tc::MODE_EMIT>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kpad * 1024));
+                std::vector<long long> hu, hid;
+                std::vector<float> hsc;
+                std::vector<int> hfl, hov;
+                for (size_t u0 = 0; u0 < n_users; u0 += fchunk) {
+                    const size_t m = std::min(fchunk, n_users - u0);
+                    hu.resize(m);
+                    for (size_t u = 0; u < m; u++)
+                        hu[u] = A_is_single_vector ? 0 : (user_ix ? (long long)user_ix[u0 + u] : (long long)(u0 + u));
+                    CK(cudaMemcpy(dusers, hu.data(), m * sizeof(long long), cudaMemcpyHostToDevice));
+                    gather_rows_kernel<real><<<(int)std::min<size_t>((m * ldf + 255) / 256, 4096), 256>>>(dA, dusers, (int)m, ldf, dAsel);
+                    LAUNCHED();
+                    tc::TileOut o = {};
+                    if (have_excl) {
+                        CK(cudaMemsetAsync(bits, 0, m * words * sizeof(uint32_t)));
+                        tc::exclusion_bitmap_kernel<IX><<<dim3(4, (unsigned)m), 128>>>(bits, words, dexp, dexi, u0, n);
+                        LAUNCHED();
+                        o.excl_bits = bits; o.excl_words = words;
+                    }
+                    o.gmax = gmax; o.ngroups = ngroups; o.tau = tau;
+                    o.cand_sc = cand_sc; o.cand_id = cand_id; o.cand_cnt = cand_cnt;
+                    const dim3 tgrid((unsigned)ntiles, (unsigned)((m + tc::TM - 1) / tc::TM));
+                    tc::score_tiles_tf32_kernel<tc::MODE_GROUPMAX><<<tgrid, 128, (size_t)kpad * 1024>>>(
+                        (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
+                    LAUNCHED();
+                    tc::select_threshold_kernel<<<(unsigned)m, 256>>>(gmax, ngroups, M_cand, tau);
+                    LAUNCHED();
+                    CK(cudaMemsetAsync(cand_cnt, 0, m * sizeof(int)));
+                    tc::score_tiles_tf32_kernel<tc::MODE_EMIT><<<tgrid, 128, (size_t)kpad * 1024>>>(
+                        (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
+                    LAUNCHED();
+                    tc::sort_candidates_kernel<<<(unsigned)m, 512>>>(cand_sc, cand_id, cand_cnt, top_sc, top_id, d_ovf);
+                    LAUNCHED();
+                    tc::rescore_select_kernel<<<(unsigned)m, 128>>>((const float*)dAsel, (const float*)dB, k, ldf, top_id,
+                                                                    top_sc, (size_t)tc::CAND_TOP, M_cand, 0, (int)n_top,
+                                                                    4e-3f, d_out_ids, d_out_sc, d_flag);
+                    LAUNCHED();
+                    CK(cudaGetLastError());
+                    hid.resize(m * n_top); hsc.resize(m * n_top); hfl.resize(m); hov.resize(m);
+                    CK(cudaMemcpy(hid.data(), d_out_ids, m * n_top * sizeof(long long), cudaMemcpyDeviceToHost));
+                    CK(cudaMemcpy(hsc.data(), d_out_sc, m * n_top * sizeof(float), cudaMemcpyDeviceToHost));
+                    CK(cudaMemcpy(hfl.data(), d_flag, m * sizeof(int), cudaMemcpyDeviceToHost));
+                    CK(cudaMemcpy(hov.data(), d_ovf, m * sizeof(int), cudaMemcpyDeviceToHost));
+                    for (size_t i = 0; i < m * n_top; i++) outp_ix[u0 * n_top + i] = (IX)hid[i];
+                    if (outp_score) for (size_t i = 0; i < m * n_top; i++) outp_score[u0 * n_top + i] = (real)hsc[i];
+                    for (size_t u = 0; u < m; u++) if (hfl[u] || hov[u]) redo.push_back(u0 + u);
+                    g_topn_stats[0] += m;
+                }
+                return 0;
+            };
+            const int frc = fused();
+            if (frc) cudaDeviceSynchronize();
+            for (void* q : mine) dfree(q);
+            return frc;
+        }
         if (use_tc) {
             CK(dmalloc(&d_out_ids, chunk * n_top * sizeof(long long)));
             CK(dmalloc(&d_out_sc, chunk * n_top * sizeof(float)));
             CK(dmalloc(&d_flag, chunk * sizeof(int)));
-            CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kpad * 1024));
+            CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel<tc::MODE_SCORES>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kpad * 1024));
         }
         CK(dmalloc(&dAsel, chunk * pitch));
         CK(dmalloc(&sc_in, chunk * n * sizeof(real))); CK(dmalloc(&sc_out, chunk * n * sizeof(real)));
@@ -1455,8 +1549,10 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             LAUNCHED();
             if (use_tc) {
                 dim3 tgrid((unsigned)((n + tc::TN - 1) / tc::TN), (unsigned)((m + tc::TM - 1) / tc::TM));
-                tc::score_tiles_tf32_kernel<<<tgrid, 128, (size_t)kpad * 1024>>>(
-                    (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, (float*)sc_in, id_in);
+                tc::TileOut o = {};
+                o.scores = (float*)sc_in; o.ids = id_in;
+                tc::score_tiles_tf32_kernel<tc::MODE_SCORES><<<tgrid, 128, (size_t)kpad * 1024>>>(
+                    (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
             } else {
                 dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 1024), (unsigned)m);
                 score_items_kernel<real><<<grid, 256, (size_t)ldf * sizeof(real)>>>(dAsel, dB, n, k, ldf, sc_in, id_in);

@@ -18,6 +18,15 @@
 // them exactly in FP32 (same left-to-right sums as the reference) and proves from the TF32 error
 // bound that no other item can enter the top N; users for which the proof fails are redone by the
 // exact scorer.  Rankings are therefore those of the exact path.
+//
+// The select is fused into the scorer's epilogue so that the U x n score matrix never exists
+// (SURVEY.md 8d).  Two passes over the tiles, the GEMM being far cheaper than any sort of n scores:
+//   pass 1 (MODE_GROUPMAX)  per user, the maximum of every group of 16 consecutive items
+//           -> tau[u] = the M-th largest group maximum (radix select over n/16 values): at least M
+//              items score >= tau[u], and at most 16 M of them unless scores tie at tau[u];
+//   pass 2 (MODE_EMIT)      items with score >= tau[u] are appended to the user's candidate list,
+// then the (<= 4096) candidates are ordered by (score desc, id asc) and the best M go to the exact
+// re-scoring as before.  Excluded items are masked in the epilogue from a per-user bitmap.
 #pragma once
 #include "common.cuh"
 
@@ -26,6 +35,14 @@ namespace tc {
 
 constexpr int TM = 128;   // users per tile  (UMMA M)
 constexpr int TN = 128;   // items per tile  (UMMA N)
+constexpr int GROUP = 16;        // items per group maximum
+constexpr int CAND_CAP = 4096;   // candidate slots per user (>= GROUP * 256)
+constexpr int CAND_TOP = 256;    // candidates handed to the exact re-scoring (>= M)
+enum { MODE_SCORES = 0, MODE_GROUPMAX = 1, MODE_EMIT = 2 };
+
+// order-preserving key of a non-negative score; masked entries (negative) sort below everything
+PMF_DEVINL uint32_t score_key(float s) { return s < 0.f ? 0u : __float_as_uint(s) + 1u; }
+PMF_DEVINL float key_score(uint32_t key) { return key == 0u ? -RealTraits<float>::huge() : __uint_as_float(key - 1u); }
 
 PMF_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,11 +128,20 @@ PMF_DEVINL void stage_operand(float4* s, const float* __restrict__ G, size_t row
     }
 }
 
-// scores[u, j] (TF32) for u in [0,U), j in [0,n); ids[u, j] = j.   grid = (ceil(n/TN), ceil(U/TM)), 128 threads.
+// What the epilogue of a tile does with its scores
+struct TileOut {
+    float* scores; int* ids;                 // MODE_SCORES: scores[u, j] (TF32), ids[u, j] = j
+    const uint32_t* excl_bits; size_t excl_words;   // bitmap of excluded items, excl_words 32-bit words per user (or null)
+    float* gmax; size_t ngroups;             // MODE_GROUPMAX: gmax[u, j / GROUP]
+    const float* tau;                        // MODE_EMIT: per-user threshold ...
+    float* cand_sc; int* cand_id; int* cand_cnt;   // ... and candidate lists (CAND_CAP slots per user)
+};
+
+// grid = (ceil(n/TN), ceil(U/TM)), 128 threads.
+template <int MODE>
 __global__ void __launch_bounds__(128) score_tiles_tf32_kernel(const float* __restrict__ Asel, int U,
                                                                const float* __restrict__ B, size_t n, int ldf,
-                                                               int kpad, float* __restrict__ scores,
-                                                               int* __restrict__ ids)
+                                                               int kpad, TileOut out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* sA = reinterpret_cast<float4*>(smem_raw);
@@ -157,15 +183,52 @@ __global__ void __launch_bounds__(128) score_tiles_tf32_kernel(const float* __re
     // epilogue: warp w owns TMEM lanes 32w .. 32w+31 (= tile rows), 32 columns at a time
     const int row = warp * 32 + lane;
     const int u = u0 + row;
+    const float NEG = -RealTraits<float>::huge();
+    uint4 ex = make_uint4(0u, 0u, 0u, 0u);       // this user's exclusion bits of the tile's 128 items
+    if (MODE != MODE_SCORES && out.excl_bits && u < U)
+        ex = __ldg(reinterpret_cast<const uint4*>(out.excl_bits + (size_t)u * out.excl_words + (j0 >> 5)));
+    const float tau = (MODE == MODE_EMIT && u < U) ? out.tau[u] : 0.f;
     for (int c = 0; c < TN / 32; c++) {
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
-        if (u < U) {
-            float* srow = scores + (size_t)u * n + j0 + c * 32;
-            int* irow = ids + (size_t)u * n + j0 + c * 32;
+        if (u >= U) continue;
+        const size_t jc = j0 + c * 32;
+        if (MODE == MODE_SCORES) {
+            float* srow = out.scores + (size_t)u * n + jc;
+            int* irow = out.ids + (size_t)u * n + jc;
 #pragma unroll
             for (int i = 0; i < 32; i++)
-                if (j0 + c * 32 + i < n) { srow[i] = __uint_as_float(r[i]); irow[i] = (int)(j0 + c * 32 + i); }
+                if (jc + i < n) { srow[i] = __uint_as_float(r[i]); irow[i] = (int)(jc + i); }
+        } else {
+            const uint32_t exw = c == 0 ? ex.x : (c == 1 ? ex.y : (c == 2 ? ex.z : ex.w));
+            // valid = inside [0, n) and not excluded
+            uint32_t valid = ~exw;
+            if (jc + 32 > n) valid &= (jc >= n) ? 0u : ((1u << (unsigned)(n - jc)) - 1u);
+            if (MODE == MODE_GROUPMAX) {
+#pragma unroll
+                for (int g = 0; g < 32 / GROUP; g++) {
+                    float m = NEG;
+#pragma unroll
+                    for (int i = 0; i < GROUP; i++) {
+                        const float v = __uint_as_float(r[g * GROUP + i]);
+                        if ((valid >> (g * GROUP + i)) & 1u) m = fmaxf(m, v);
+                    }
+                    const size_t gi = jc / GROUP + g;
+                    if (gi < out.ngroups) out.gmax[(size_t)u * out.ngroups + gi] = m;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const float v = __uint_as_float(r[i]);
+                    if (((valid >> i) & 1u) && v >= tau) {
+                        const int pos = atomicAdd(out.cand_cnt + u, 1);
+                        if (pos < CAND_CAP) {
+                            out.cand_sc[(size_t)u * CAND_CAP + pos] = v;
+                            out.cand_id[(size_t)u * CAND_CAP + pos] = (int)(jc + i);
+                        }
+                    }
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -234,6 +297,96 @@ __global__ void __launch_bounds__(128) rescore_select_kernel(const float* __rest
         }
         flag[u] = bad;
     }
+}
+
+// bits[u, j] = 1 for every item j in user (user0 + u)'s exclusion list.  grid = (x, users of the chunk)
+template <class IX>
+__global__ void exclusion_bitmap_kernel(uint32_t* __restrict__ bits, size_t words, const IX* __restrict__ excl_ptr,
+                                        const IX* __restrict__ excl_ix, size_t user0, size_t n)
+{
+    const size_t u = blockIdx.y;
+    const size_t beg = (size_t)excl_ptr[user0 + u], end = (size_t)excl_ptr[user0 + u + 1];
+    for (size_t t = beg + blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < end; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = (size_t)excl_ix[t];
+        if (j < n) atomicOr(bits + u * words + (j >> 5), 1u << (j & 31));
+    }
+}
+
+// tau[u] = the M-th largest of the user's group maxima (most-significant-digit radix select on the
+// order-preserving keys, 8 bits a round).  One CTA of 256 threads per user.
+__global__ void __launch_bounds__(256) select_threshold_kernel(const float* __restrict__ gmax, size_t ngroups, int M,
+                                                               float* __restrict__ tau)
+{
+    __shared__ unsigned int hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_want;
+    const float* g = gmax + (size_t)blockIdx.x * ngroups;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_prefix = 0u; s_want = M; }
+    uint32_t mask = 0u;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        for (size_t i = tid; i < ngroups; i += 256) {
+            const uint32_t key = score_key(g[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {     // walk the digits from the top until `want` keys have been passed
+            int want = s_want, d = 255;
+            for (; d > 0; d--) {
+                const int c = (int)hist[d];
+                if (c >= want) break;
+                want -= c;
+            }
+            s_prefix = prefix | ((uint32_t)d << shift);
+            s_want = want;
+        }
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    if (tid == 0) tau[blockIdx.x] = key_score(s_prefix);
+}
+
+// Order one user's candidates by (score desc, id asc) and keep the best CAND_TOP (padded with -huge).
+// overflow[u] = 1 when more than CAND_CAP items reached the threshold (ties at tau): redo exactly.
+__global__ void __launch_bounds__(512) sort_candidates_kernel(const float* __restrict__ cand_sc,
+                                                              const int* __restrict__ cand_id,
+                                                              const int* __restrict__ cand_cnt,
+                                                              float* __restrict__ top_sc, int* __restrict__ top_id,
+                                                              int* __restrict__ overflow)
+{
+    __shared__ float ss[CAND_CAP];
+    __shared__ int si[CAND_CAP];
+    const int u = blockIdx.x, tid = threadIdx.x;
+    const int cnt = cand_cnt[u];
+    const float NEG = -RealTraits<float>::huge();
+    const int m = cnt < CAND_CAP ? cnt : CAND_CAP;
+    int len_pad = CAND_TOP;                          // sort only as much as is filled (power of two)
+    while (len_pad < m) len_pad <<= 1;
+    for (int c = tid; c < len_pad; c += blockDim.x) {
+        ss[c] = c < m ? cand_sc[(size_t)u * CAND_CAP + c] : NEG;
+        si[c] = c < m ? cand_id[(size_t)u * CAND_CAP + c] : 0x7fffffff;
+    }
+    __syncthreads();
+    for (int len = 2; len <= len_pad; len <<= 1)
+        for (int j = len >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < len_pad / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (j - 1)), hi = lo + j;
+                const bool desc_block = ((lo & len) == 0);
+                const float s0 = ss[lo], s1 = ss[hi];
+                const int i0 = si[lo], i1 = si[hi];
+                const bool before = (s0 > s1) || (s0 == s1 && i0 < i1);
+                if (before != desc_block) { ss[lo] = s1; ss[hi] = s0; si[lo] = i1; si[hi] = i0; }
+            }
+            __syncthreads();
+        }
+    for (int c = tid; c < CAND_TOP; c += blockDim.x) {
+        top_sc[(size_t)u * CAND_TOP + c] = ss[c];
+        top_id[(size_t)u * CAND_TOP + c] = si[c];
+    }
+    if (tid == 0) overflow[u] = cnt > CAND_CAP ? 1 : 0;
 }
 
 __global__ void any_negative_kernel(const float* __restrict__ x, size_t n, int* __restrict__ flag)

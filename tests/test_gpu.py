@@ -569,6 +569,42 @@ def test_topn_batch_tensor_core_path_is_exact(k, n_top):
         assert not np.isin(ix[u], ex).any()
 
 
+def test_topn_fused_select_edge_cases(monkeypatch):
+    """The fused select (group maxima -> threshold -> candidates) against the full-sort path and the
+    oracle: items sorted by popularity (the worst case for group maxima), an item count that is not a
+    multiple of the tile, unsorted exclusion lists, and massive score ties (candidate overflow ->
+    exact fallback)."""
+    from poismf_b200 import _lib, c_funs
+    rng = np.random.default_rng(21)
+    k, n_items, n_users, n_top = 40, 30_001, 260, 50
+    A = np.ascontiguousarray(rng.gamma(0.5, 0.5, size=(n_users, k)).astype(np.float32))
+    pop = np.sort(rng.pareto(1.5, n_items))[::-1].astype(np.float32)          # descending popularity
+    B = np.ascontiguousarray((rng.gamma(2.0, 0.5, size=(n_items, k)) * pop[:, None]).astype(np.float32))
+    lens = rng.integers(0, 200, n_users)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    eix = np.concatenate([rng.choice(400, int(m), replace=False) for m in lens]).astype(np.uint64)  # unsorted, popular
+    _lib.topn_stats(reset=True)
+    ix, sc = c_funs._topN_batch(A, B, excl_ptr=ptr, excl_ix=eix, top_n=n_top, output_score=True)
+    n_tc, n_redo = _lib.topn_stats(reset=True)
+    assert n_tc == n_users and n_redo <= 0.1 * n_users
+    monkeypatch.setenv("POISMF_B200_TOPN_SORT", "1")                           # full-sort path
+    ix2, sc2 = c_funs._topN_batch(A, B, excl_ptr=ptr, excl_ix=eix, top_n=n_top, output_score=True)
+    monkeypatch.delenv("POISMF_B200_TOPN_SORT")
+    assert np.array_equal(sc, sc2)
+    assert all((sc[u] == sc[u][t]).sum() > 1 for u, t in zip(*np.nonzero(ix != ix2)))
+    orc = Restatement(np.float32)
+    for u in range(0, n_users, 13):
+        ex = eix[int(ptr[u]):int(ptr[u + 1])]
+        rc, ix_r, sc_r = orc.topN(np.ascontiguousarray(A[u]), B, n_top, exclude=ex if ex.size else None)
+        assert rc == 0 and np.array_equal(sc[u], sc_r) and not np.isin(ix[u], ex).any()
+    # ties: every item scores the same for every user -> more candidates than slots -> exact fallback
+    Bt = np.ascontiguousarray(np.tile(B[:1], (n_items, 1)))
+    _lib.topn_stats(reset=True)
+    ix3, sc3 = c_funs._topN_batch(A[:8], Bt, top_n=n_top, output_score=True)
+    assert _lib.topn_stats(reset=True)[1] == 8
+    assert all(len(set(r.tolist())) == n_top for r in ix3) and (sc3 == sc3[:, :1]).all()
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_very_heavy_columns_streaming_clusters(dtype):
     """A handful of items with ~1e4 non-zeros each: every column is a 16-CTA cluster row whose slices
