@@ -194,3 +194,45 @@ class GpuBackend:
             k = self.k
             return self.A[:, :k].cpu().numpy(), self.B[:, :k].cpu().numpy()
         return self.fit.get_factors()
+
+
+def user_ranges(n_users, nparts):
+    """Contiguous, near-equal user ranges (topN work per user is the same: n items x k)."""
+    cuts = [n_users * p // nparts for p in range(nparts + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in range(nparts)]
+
+
+def topn_sharded(A, B, top_n, users=None, excl_ptr=None, excl_ix=None, output_score=False, rank=0, world=1,
+                 group=None, scorer=None):
+    """Batched topN with the USERS split across ranks: B is replicated, every rank ranks
+    its own contiguous range of users on its GPU, and the per-user lists are all-gathered — no exchange
+    inside the scoring.  Every rank returns the full (n_users x top_n) result.
+
+    `scorer(A, B, users, excl_ptr, excl_ix, top_n, output_score) -> (ids, scores)` defaults to the
+    device path (c_funs._topN_batch); the CPU tests inject a stand-in."""
+    if scorer is None:
+        from . import c_funs
+        scorer = lambda A_, B_, u_, p_, i_, n_, s_: c_funs._topN_batch(A_, B_, users=u_, excl_ptr=p_, excl_ix=i_,
+                                                                     top_n=n_, output_score=s_)
+    all_users = np.arange(A.shape[0], dtype=np.uint64) if users is None else np.ascontiguousarray(users, dtype=np.uint64)
+    lo, hi = user_ranges(all_users.shape[0], world)[rank]
+    mine = np.ascontiguousarray(all_users[lo:hi])
+    p_loc = i_loc = None
+    if excl_ptr is not None and excl_ix is not None:
+        ep = np.asarray(excl_ptr).astype(np.int64)
+        p_loc = np.ascontiguousarray(ep[lo:hi + 1] - ep[lo]).astype(np.uint64)
+        i_loc = np.ascontiguousarray(np.asarray(excl_ix)[ep[lo]:ep[hi]]).astype(np.uint64)
+    if hi > lo:
+        ids, sc = scorer(A, B, mine, p_loc, i_loc, top_n, output_score)
+    else:
+        ids = np.empty((0, top_n), np.uint64)
+        sc = np.empty((0, top_n) if output_score else (0, 0), B.dtype)
+    if world == 1:
+        return ids, sc
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, (ids, sc), group=group)
+    ids = np.concatenate([p[0] for p in parts], axis=0)
+    sc = np.concatenate([p[1] for p in parts], axis=0) if output_score else parts[0][1]
+    return ids, sc
+

@@ -368,6 +368,53 @@ def test_two_gpu_sharded_matches_single_gpu(exchange):
             assert np.array_equal(res[r][case][0], A) and np.array_equal(res[r][case][1], B), (case, r)
 
 
+def _two_gpu_topn_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from poismf_b200.sharding import topn_sharded
+    torch.cuda.set_device(rank)
+    os.environ["POISMF_B200_DEVICE"] = str(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    A, B, ptr, eix = _topn_case()
+    ids, sc = topn_sharded(A, B, 20, excl_ptr=ptr, excl_ix=eix, output_score=True, rank=rank, world=world)
+    q.put((rank, ids, sc))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _topn_case():
+    rng = np.random.default_rng(31)
+    A = np.ascontiguousarray(rng.gamma(0.5, 0.5, size=(301, 32)).astype(np.float32))
+    B = np.ascontiguousarray(rng.gamma(0.5, 0.5, size=(20_000, 32)).astype(np.float32))
+    lens = rng.integers(0, 50, A.shape[0])
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    eix = np.concatenate([rng.choice(B.shape[0], int(m), replace=False) for m in lens]).astype(np.uint64)
+    return A, B, ptr, eix
+
+
+def test_two_gpu_user_sharded_topn_matches_single_gpu():
+    """topN shards by users, B replicated, no exchange inside the scoring."""
+    import torch
+    from poismf_b200 import c_funs
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_gpu_topn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    A, B, ptr, eix = _topn_case()
+    ids, sc = c_funs._topN_batch(A, B, excl_ptr=ptr, excl_ix=eix, top_n=20, output_score=True)
+    for _, i2, s2 in res:
+        assert np.array_equal(i2, ids) and np.array_equal(s2, sc)
+
+
 # ---------------------------------------------------------------- the other BASELINE shapes, scaled down
 def test_netflix_shaped_tncg_k100():
     """BASELINE config #3 shape at 1/100 scale: few, very long columns (every column is a

@@ -173,3 +173,47 @@ def test_sharded_sweep_gloo_world2(case):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def _gloo_topn_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle.oracle import Restatement
+    from poismf_b200.sharding import topn_sharded
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(4)
+    n_users, n_items, k, n_top = 37, 500, 6, 9
+    A = rng.gamma(1, 1, size=(n_users, k)); B = rng.gamma(1, 1, size=(n_items, k))
+    users = rng.permutation(n_users)[:30].astype(np.uint64)
+    lens = rng.integers(0, 20, users.shape[0])
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    eix = np.concatenate([np.sort(rng.choice(n_items, int(m), replace=False)) for m in lens]).astype(np.uint64)
+    orc = Restatement(np.float64)
+
+    def cpu_scorer(A_, B_, u_, p_, i_, n_, s_):            # test infrastructure: the oracle, user by user
+        ids = np.empty((u_.shape[0], n_), np.uint64); sc = np.empty((u_.shape[0], n_))
+        for j, usr in enumerate(u_):
+            ex = i_[int(p_[j]):int(p_[j + 1])]
+            _, ids[j], sc[j] = orc.topN(np.ascontiguousarray(A_[int(usr)]), B_, n_, exclude=ex if ex.size else None)
+        return ids, sc
+
+    ids, sc = topn_sharded(A, B, n_top, users=users, excl_ptr=ptr, excl_ix=eix, output_score=True, rank=rank,
+                           world=world, scorer=cpu_scorer)
+    ids1, sc1 = topn_sharded(A, B, n_top, users=users, excl_ptr=ptr, excl_ix=eix, output_score=True, scorer=cpu_scorer)
+    q.put((rank, bool(np.array_equal(ids, ids1) and np.array_equal(sc, sc1) and ids.shape == (30, n_top))))
+    dist.destroy_process_group()
+
+
+def test_topn_user_sharding_gloo_world2():
+    """topN shards by users with B replicated: two ranks' gathered lists == one rank's."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_topn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
