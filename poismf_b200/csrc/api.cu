@@ -630,7 +630,12 @@ template <class real> struct HandleT : pmf_b200_handle {
         CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
         if (hc.early_stop) CK(cudaMemsetAsync(d_unchanged, 0, sizeof(unsigned long long), stream));
 
-        const bool overlap = !profiling && !getenv("POISMF_B200_SERIAL_BINS");
+        // tncg bins run one after the other on the handle's stream: with its bins spread over the side
+        // streams the double-precision tncg kernels faulted on the 45k x 20k problem (r1, unexplained:
+        // clean under compute-sanitizer, with blocking launches and on one stream); POISMF_B200_TN_OVERLAP=1
+        // restores the overlap for debugging
+        const bool overlap = !profiling && !getenv("POISMF_B200_SERIAL_BINS") &&
+                             (p.method != PMF_TNCG || getenv("POISMF_B200_TN_OVERLAP"));
         if (overlap) CK(cudaEventRecord(ev_fork, stream));
         int n_launched = 0;
         bool used[NAUX] = {};
@@ -639,7 +644,12 @@ template <class real> struct HandleT : pmf_b200_handle {
             if (b.rows.empty()) continue;
             cudaStream_t ls = stream;
             if (overlap) {
-                const int si = n_launched % NAUX;
+                static const int n_streams = []() {   // debugging: POISMF_B200_STREAMS=1..6 side streams
+                    const char* e = getenv("POISMF_B200_STREAMS");
+                    const int v = e ? atoi(e) : NAUX;
+                    return v < 1 ? 1 : (v > NAUX ? NAUX : v);
+                }();
+                const int si = n_launched % n_streams;
                 ls = aux[si];
                 if (!used[si]) { CK(cudaStreamWaitEvent(ls, ev_fork, 0)); used[si] = true; }
             }
@@ -683,7 +693,9 @@ template <class real> struct HandleT : pmf_b200_handle {
             else
                 e = strict ? launch_rows_pgcg_strict<real>(cfg, P) : launch_rows_pgcg_fast<real>(cfg, P);
             LAUNCHED();
-            if (e != cudaSuccess) return fail("row kernel launch failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess)
+                return fail("row kernel launch failed at side %d bin %d (block %d cluster %d cap %d threads %d smem %zu): %s",
+                            side, bi, (int)b.block, b.cluster, b.cap, b.threads, b.smem, cudaGetErrorString(e));
             if (profiling) {
                 CK(cudaEventRecord(ev1, stream));
                 S.bins[bi].ev.push_back(ev0); S.bins[bi].ev.push_back(ev1);

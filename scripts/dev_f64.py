@@ -9,7 +9,7 @@ dtype = np.float64
 csr, csc, A0, B0 = bench.make_problem(cfg, dtype)
 print("max row", np.diff(csr[1].astype(np.int64)).max(), "max col", np.diff(csc[1].astype(np.int64)).max(), flush=True)
 method = sys.argv[1]
-hp = {"pg": dict(l2_reg=1e9, step_size=1e-7, maxupd=1), "cg": dict(l2_reg=1e4, maxupd=5, limit_step=True), "tncg": dict(l2_reg=1e3, maxupd=750)}[method]
+hp = {"pg": dict(l2_reg=1e9, step_size=1e-7, maxupd=1), "cg": dict(l2_reg=1e4, maxupd=5, limit_step=True), "tncg": dict(l2_reg=1e3, maxupd=int(os.environ.get("MAXUPD", "750")))}[method]
 fit = DeviceFit(cfg["dimA"], cfg["dimB"], cfg["k"], dtype, device=0)
 if os.environ.get("TORCHSTREAM"):
     import torch
