@@ -630,12 +630,7 @@ template <class real> struct HandleT : pmf_b200_handle {
         CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
         if (hc.early_stop) CK(cudaMemsetAsync(d_unchanged, 0, sizeof(unsigned long long), stream));
 
-        // tncg bins run one after the other on the handle's stream: with its bins spread over the side
-        // streams the double-precision tncg kernels faulted on the 45k x 20k problem (r1, unexplained:
-        // clean under compute-sanitizer, with blocking launches and on one stream); POISMF_B200_TN_OVERLAP=1
-        // restores the overlap for debugging
-        const bool overlap = !profiling && !getenv("POISMF_B200_SERIAL_BINS") &&
-                             (p.method != PMF_TNCG || getenv("POISMF_B200_TN_OVERLAP"));
+        const bool overlap = !profiling && !getenv("POISMF_B200_SERIAL_BINS");
         if (overlap) CK(cudaEventRecord(ev_fork, stream));
         int n_launched = 0;
         bool used[NAUX] = {};

@@ -268,7 +268,12 @@ PMF_DEVINL real vdot(const Team& tm, const real* x, const real* y, int k)
     }
     real s = 0;
     for (int i = tm.kbegin(); i < k; i += tm.kstride()) s = fma(x[i], y[i], s);
-    return tm.ksum(s);
+    s = tm.ksum(s);
+    // CTA / cluster teams: every warp computes the sum redundantly and at its own pace; nobody may
+    // overwrite x or y before the slowest warp has read them (a warp that saw a half-updated vector
+    // would leave the replicated control flow: found by racecheck in tn_linesearch, r1)
+    if (Team::k_bcast) tm.sync();
+    return s;
 }
 // sqrt(sum x^2) — the shim's nrm2 (oracle/blas_shim.c)
 template <bool STRICT, class real, class Team>

@@ -441,19 +441,22 @@ def test_netflix_shaped_tncg_k100():
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_midsize_tncg_all_bins_populated(dtype):
     """1/8-scale config #2 (45k x 20k, 1.9M nnz, k=50): every bin of the planner is populated at once
-    (sub-warp ... streaming clusters).  Regression test for a fault of the double-precision tncg kernels
-    when their bins were spread over the side streams (r1): the sweep must complete, stay finite and
-    non-negative, and raise the log-likelihood over the initial factors."""
+    (sub-warp ... streaming clusters).  Regression test for a shared-memory race of the CTA / cluster
+    teams in the tncg line search (a warp overwrote a vector another warp was still summing; the
+    double-precision kernels then faulted on this problem, r1): the sweep must complete, stay finite
+    and non-negative, and raise the log-likelihood over the initial factors."""
     from poismf_b200.synth import init_factors, powerlaw_counts
     dimA, dimB, k = 45_000, 20_000, 50
     csr, csc = powerlaw_counts(dimA, dimB, 2_200_000, dtype=dtype, seed=1)
     A0, B0 = init_factors(dimA, dimB, k, seed=1, dtype=dtype)
     kw = dict(l2_reg=1e3, maxupd=20, numiter=1)
-    A, B = A0.copy(), B0.copy()
-    assert run_device(csr, csc, A, B, "tncg", kw) == 0
-    assert np.isfinite(A).all() and np.isfinite(B).all() and (A >= 0).all() and (B >= 0).all()
     orc = Restatement(dtype)
-    assert orc.llk(A, B, csr) > orc.llk(A0, B0, csr)
+    l0 = orc.llk(A0, B0, csr)
+    for _ in range(2):
+        A, B = A0.copy(), B0.copy()
+        assert run_device(csr, csc, A, B, "tncg", kw) == 0
+        assert np.isfinite(A).all() and np.isfinite(B).all() and (A >= 0).all() and (B >= 0).all()
+        assert orc.llk(A, B, csr) > l0
 
 
 def test_webscale_shaped_pg_k64():
