@@ -183,6 +183,7 @@ template <class real> struct HandleT : pmf_b200_handle {
     // small or latency-bound bins overlap (fork from / join to the handle's stream with events)
     real* peer[2][7] = {};      // peers' replicas of A (0) and B (1), opened through CUDA IPC
     int npeers[2] = {0, 0};
+    bool exported[2] = {false, false};   // A / B handed to other processes: never recycled through the block cache
     static constexpr int NAUX = 6;
     cudaStream_t aux[NAUX] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
@@ -197,8 +198,10 @@ template <class real> struct HandleT : pmf_b200_handle {
         cudaSetDevice(device);
         sync_all();
         sides[0].free_all(); sides[1].free_all();
-        if (ownA && A) dfree(A);
-        if (ownB && B) dfree(B);
+        for (int w = 0; w < 2; w++)
+            for (int q = 0; q < npeers[w]; q++) cudaIpcCloseMemHandle(peer[w][q]);
+        if (ownA && A) { if (exported[0]) DevPool::get().discard(A); else dfree(A); }
+        if (ownB && B) { if (exported[1]) DevPool::get().discard(B); else dfree(B); }
         if (csum) dfree(csum);
         if (partial) dfree(partial);
         if (counters) dfree(counters);
@@ -359,8 +362,8 @@ template <class real> struct HandleT : pmf_b200_handle {
     {
         CK(cudaSetDevice(device));
         if (sync_all()) return 1;
-        if (Ad) { if (ownA && A) dfree(A); A = (real*)Ad; ownA = false; }
-        if (Bd) { if (ownB && B) dfree(B); B = (real*)Bd; ownB = false; }
+        if (Ad) { if (ownA && A) { if (exported[0]) DevPool::get().discard(A); else dfree(A); } A = (real*)Ad; ownA = false; }
+        if (Bd) { if (ownB && B) { if (exported[1]) DevPool::get().discard(B); else dfree(B); } B = (real*)Bd; ownB = false; }
         return 0;
     }
     void* factor_ptr(int which) override { return which == 0 ? (void*)A : (void*)B; }
@@ -716,6 +719,7 @@ template <class real> struct HandleT : pmf_b200_handle {
             return fail("ipc_export: factors are bound to caller memory; export needs handle-owned buffers");
         cudaIpcMemHandle_t hd;
         CK(cudaIpcGetMemHandle(&hd, which == 0 ? (void*)A : (void*)B));
+        exported[which] = true;
         static_assert(sizeof(hd) == PMF_B200_IPC_HANDLE_BYTES, "IPC handle size");
         memcpy(out, &hd, sizeof hd);
         return 0;
@@ -724,6 +728,7 @@ template <class real> struct HandleT : pmf_b200_handle {
     {
         CK(cudaSetDevice(device));
         if (n_ranks < 1 || n_ranks > 8) return fail("ipc_import: 1..8 ranks");
+        for (int q = 0; q < npeers[which]; q++) cudaIpcCloseMemHandle(peer[which][q]);
         npeers[which] = 0;
         for (int r = 0; r < n_ranks; r++) {
             if (r == self_rank) continue;

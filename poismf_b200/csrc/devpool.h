@@ -79,6 +79,17 @@ public:
         if (cur != key.first) cudaSetDevice(cur);
     }
 
+    // release a block for good (never cached): memory other processes have mapped through CUDA IPC
+    void discard(void* p)
+    {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            live_.erase(p);
+        }
+        cudaFree(p);
+    }
+
     // cudaFree every idle block of `dev` (all devices if dev < 0); returns the bytes released
     size_t release(int dev)
     {
