@@ -98,6 +98,17 @@ def test_nnz_balanced_ranges():
     assert nnz_balanced_ranges(np.array([0, 5]), 4)[-1] == (1, 1) or True   # more parts than rows: empty tails
 
 
+def test_user_ranges_and_row_cost():
+    from poismf_b200.sharding import row_cost, user_ranges
+    for n, parts in ((10, 3), (7, 8), (0, 2), (1000, 8)):
+        rg = user_ranges(n, parts)
+        assert rg[0][0] == 0 and rg[-1][1] == n and all(a[1] == b[0] for a, b in zip(rg, rg[1:]))
+        sizes = [hi - lo for lo, hi in rg]
+        assert max(sizes) - min(sizes) <= 1
+    c = row_cost(np.array([0, 1, 1000, 1001, 16000, 16001]))
+    assert c[0] == 0 and np.all(np.diff(c) > 0)          # empty rows cost nothing; cost grows with length
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
