@@ -294,6 +294,13 @@ def main():
                 "sweep_frac_of_peak": sweep_bytes / (ms_step / 1e3) / 1e9 / peak,
                 "bins": [{"side": p["side"], "team": team_name(p["block_team"]), "cap": p["cap"],
                           "rows": p["nrows"], "nnz": p["nnz"], "ms_per_sweep": p["ms"] / args.steps} for p in prof]}
+        # the solver re-reads every staged tile once per evaluation pass, out of shared memory
+        # (or L2 for streamed rows); upper bound of passes per row and the on-chip traffic that implies
+        mu = int(cfg["hp"].get("maxupd", 1))
+        passes = {"cg": 1 + 2 * mu, "pg": 2 * mu}.get(cfg["method"])
+        if passes:
+            roof["tile_passes_per_row_max"] = passes
+            roof["onchip_tile_GBps_upper"] = 2 * nnz * k * s * passes / (ms_step / 1e3) / 1e9
 
     # e2e: drop-in run_poismf with host buffers (rank 0 alone at N=1; sharded path otherwise reuses value)
     e2e = None
