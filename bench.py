@@ -173,7 +173,7 @@ def main():
         ms, nnz, info = run_reference(cfg, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "nnz processed/sec per alternating sweep", "value": info["value"],
                 "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_line, "cpu_baseline": info,
                 "e2e": {"value": info["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
