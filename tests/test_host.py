@@ -50,6 +50,24 @@ def test_no_cpu_fallback():
     rc = L.run_poismf(p(A), p(csr[0]), p(csr[1]), p(csr[2]), p(B), p(csc[0]), p(csc[1]), p(csc[2]),
                       100, 1000, 5, 1e9, 0., 1., 1e-7, 3, False, 1, 1, False, False, True, 1)
     assert rc == 1 and np.array_equal(A, A0)
+    # the entry points added around the path refuse as well
+    rows = np.repeat(np.arange(100, dtype=np.uint64), np.diff(csr[1].astype(np.int64)))
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        c_funs._fit_coo(rows, csr[2], csr[0], A0.copy(), B0.copy(), method="pg")
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        c_funs._coo_to_csr_csc(rows, csr[2], csr[0], 100, 1000)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        c_funs._predict_factors(csr[0][:3], csr[2][:3], B0, B0.sum(0), A0.mean(0))
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        c_funs._topN_batch(A0, B0, top_n=5)
+    from poismf_b200 import _lib
+    Lb = _lib.lib()
+    out = np.zeros(5)
+    assert Lb.pmf_b200_factors_single(1, 8, p(out), 5, p(A0[0].copy()), 1, p(csr[0]), p(csr[2]), 3, p(B0),
+                                      p(B0.sum(0)), 10, 1e3, 0., 0., 1., 0) == 1
+    assert Lb.pmf_b200_fit_coo(1, 8, p(A), p(B), p(rows), p(csr[2]), p(csr[0]), rows.shape[0], 100, 1000, 5,
+                               1e9, 0., 1., 1e-7, 3, 0, 1, 1, 0, 0, 0) == 1
+    assert np.array_equal(A, A0) and not out.any()
 
 
 def test_argument_validation_mirrors_wrapper():
