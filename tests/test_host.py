@@ -116,6 +116,31 @@ def test_nnz_balanced_ranges():
     assert nnz_balanced_ranges(np.array([0, 5]), 4)[-1] == (1, 1) or True   # more parts than rows: empty tails
 
 
+def test_devpool_size_classes(tmp_path):
+    """The device block cache hands out size classes: never smaller than the request, at most 12.5 %
+    (and 256 MB) larger, and requests of one class map to one block size (host-only check of
+    poismf_b200/csrc/devpool.h; no CUDA call is made)."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++", path="/usr/bin:" + os.environ.get("PATH", "")) or shutil.which("c++")
+    cuda_inc = "/usr/local/cuda/include"
+    if cxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs a host C++ compiler and the CUDA headers")
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "devpool.h"\n#include <cstdio>\n#include <cstdlib>\n'
+                   'int main(int c, char** v) { for (int i = 1; i < c; i++) '
+                   'printf("%zu\\n", pmf::DevPool::size_class((size_t)strtoull(v[i], 0, 10))); return 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.run([cxx, "-std=c++17", "-I", cuda_inc, "-I", os.path.join(ROOT, "poismf_b200", "csrc"),
+                    str(src), "-o", str(exe)], check=True)
+    req = [1, 511, 512, 513, 5000, 2**20, 2**20 + 1, 72_000_000, 3 * 2**30, 48 * 2**30 + 12345]
+    got = [int(x) for x in subprocess.run([str(exe)] + [str(r) for r in req], check=True,
+                                          capture_output=True, text=True).stdout.split()]
+    for r, g in zip(req, got):
+        assert g >= max(r, 512) and g - r <= max(512, r // 8, 0) and g - r <= 256 * 2**20, (r, g)
+    assert got[0] == got[1] == got[2] == 512 and got[3] == 1024 and got[5] == 2**20
+
+
 def test_user_ranges_and_row_cost():
     from poismf_b200.sharding import row_cost, user_ranges
     for n, parts in ((10, 3), (7, 8), (0, 2), (1000, 8)):
