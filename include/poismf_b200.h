@@ -115,7 +115,12 @@ int pmf_b200_set_profiling(pmf_b200_handle* h, int on);                       /*
 int pmf_b200_get_profile(pmf_b200_handle* h, pmf_b200_bin_profile* out, int max_entries);  /* returns #entries */
 
 /* ---- drop-in entry points (host pointers in, host pointers out) ---------- */
-/* Replaces run_poismf, src/poismf.c:435-632 (prototype src/poismf.h:226-233). */
+/* Replaces run_poismf, src/poismf.c:435-632 (prototype src/poismf.h:226-233).  Stateless like the
+ * reference: everything is uploaded, swept and downloaded inside the call.  The transfers are
+ * pipelined against the half-sweeps (CSR goes up behind the first B half-sweep, B comes down behind
+ * the last A half-sweep), pageable buffers are staged by host threads, and the device blocks go
+ * back to a per-process cache (pmf_b200_release_cache).  With env POISMF_B200_CACHE_X=1 the
+ * uploaded matrix is kept for the next call on the same arrays. */
 int pmf_b200_run_poismf(int dtype, int index_bytes,
                         void* A, const void* Xr, const void* Xr_indptr, const void* Xr_indices,
                         void* B, const void* Xc, const void* Xc_indptr, const void* Xc_indices,
