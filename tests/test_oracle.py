@@ -118,3 +118,34 @@ def test_factors_single_restatement(dtype, case):
         for j, r in enumerate(FS_ROWS):
             assert np.array_equal(A[r], got[j])
 
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(24))
+def test_restatement_matches_reference_on_random_small_problems(seed):
+    """Random shapes (incl. k = 1, k not a multiple of 4, empty rows/columns), random method and
+    hyper-parameters: the restatement and the reference build agree bit for bit in both dtypes."""
+    from poismf_b200.synth import init_factors, powerlaw_counts
+    rng = np.random.default_rng(1000 + seed)
+    dimA, dimB = int(rng.integers(3, 70)), int(rng.integers(3, 90))
+    k = int(rng.choice([1, 2, 3, 5, 8, 13]))
+    nnz = int(rng.integers(1, dimA * dimB // 2 + 2))
+    method = ["pg", "cg", "tncg"][seed % 3]
+    kw = dict(l2_reg=float(10.0 ** rng.uniform(0, 5)), l1_reg=float(rng.choice([0.0, 0.3])),
+              w_mult=float(rng.choice([1.0, 0.5, 2.5])), numiter=int(rng.integers(1, 4)))
+    if method == "pg":
+        kw.update(step_size=float(10.0 ** rng.uniform(-7, -3)), maxupd=int(rng.integers(1, 4)))
+    elif method == "cg":
+        kw.update(maxupd=int(rng.integers(1, 8)), limit_step=bool(rng.integers(0, 2)))
+    else:
+        kw.update(maxupd=int(rng.integers(1, 15 * k + 1)), reuse_prev=bool(rng.integers(0, 2)),
+                  early_stop=bool(rng.integers(0, 2)))
+    for dtype in DTYPES:
+        csr, csc = powerlaw_counts(dimA, dimB, nnz, alpha_a=float(rng.uniform(0.2, 1.2)),
+                                   alpha_b=float(rng.uniform(0.2, 1.2)), dtype=dtype, seed=seed)
+        A0, B0 = init_factors(dimA, dimB, k, dtype=dtype, seed=seed)
+        A1, B1, A2, B2 = A0.copy(), B0.copy(), A0.copy(), B0.copy()
+        rc1 = Ref(dtype).run_poismf(A1, B1, csr, csc, method, **kw)
+        rc2 = Restatement(dtype).run_poismf(A2, B2, csr, csc, method, **kw)
+        assert rc1 == rc2 == 0
+        assert np.array_equal(A1, A2, equal_nan=True) and np.array_equal(B1, B2, equal_nan=True), (method, kw)
+
