@@ -149,3 +149,46 @@ def test_restatement_matches_reference_on_random_small_problems(seed):
         assert rc1 == rc2 == 0
         assert np.array_equal(A1, A2, equal_nan=True) and np.array_equal(B1, B2, equal_nan=True), (method, kw)
 
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(12))
+def test_restatement_inference_paths_on_random_problems(seed):
+    """factors_multiple, factors_single, predict_multiple and topN (include / exclude lists) of the
+    restatement against the reference build on random inputs, bit for bit."""
+    from poismf_b200.synth import powerlaw_counts
+    rng = np.random.default_rng(2000 + seed)
+    dimA, dimB = int(rng.integers(2, 40)), int(rng.integers(12, 120))
+    k = int(rng.choice([1, 3, 4, 7, 10]))
+    method = ["pg", "cg", "tncg"][seed % 3]
+    for dtype in DTYPES:
+        csr, _ = powerlaw_counts(dimA, dimB, int(rng.integers(1, dimA * dimB // 3 + 2)), dtype=dtype, seed=seed)
+        B = np.ascontiguousarray(rng.gamma(1, 0.3, size=(dimB, k)).astype(dtype))
+        Bsum = np.ascontiguousarray((B.sum(0) + 0.05).astype(dtype))
+        Amean = np.ascontiguousarray(rng.gamma(1, 0.3, size=k).astype(dtype))
+        kw = dict(l2_reg=float(10.0 ** rng.uniform(0, 4)), w_mult=float(rng.choice([1.0, 2.0])),
+                  niter=int(rng.integers(1, 4)), maxupd=int(rng.integers(1, 6)), step_size=1e-4,
+                  limit_step=bool(rng.integers(0, 2)), reuse_mean=bool(rng.integers(0, 2)))
+        r1, A1 = Ref(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
+        r2, A2 = Restatement(dtype).factors_multiple(B, Bsum, Amean, csr, method, **kw)
+        assert r1 == r2 == 0 and np.array_equal(A1, A2, equal_nan=True), ("factors_multiple", method, kw)
+        row = int(rng.integers(0, dimA))
+        c, ix = fs_row(csr, row)
+        fkw = dict(reuse_mean=kw["reuse_mean"], maxupd=int(rng.integers(1, 40)), l2_reg=kw["l2_reg"],
+                   l1_new=float(rng.choice([0.0, 0.4])), l1_old=float(rng.choice([0.0, 0.1])), w_mult=kw["w_mult"])
+        assert np.array_equal(Ref(dtype).factors_single(c, ix, B, Bsum, Amean, **fkw)[1],
+                              Restatement(dtype).factors_single(c, ix, B, Bsum, Amean, **fkw)[1], equal_nan=True)
+        A = np.ascontiguousarray(rng.gamma(1, 0.3, size=(dimA, k)).astype(dtype))
+        ixA = rng.integers(0, dimA, 50).astype(np.uint64); ixB = rng.integers(0, dimB, 50).astype(np.uint64)
+        assert np.array_equal(Ref(dtype).predict_multiple(A, B, ixA, ixB),
+                              Restatement(dtype).predict_multiple(A, B, ixA, ixB))
+        n_top = int(rng.integers(1, 8))
+        a = np.ascontiguousarray(A[0])
+        excl = np.sort(rng.choice(dimB, int(rng.integers(1, dimB - n_top)), replace=False)).astype(np.uint64)
+        incl = rng.choice(dimB, int(rng.integers(n_top, dimB)), replace=False).astype(np.uint64)
+        for lists in (dict(), dict(exclude=excl), dict(include=incl)):
+            t1 = Ref(dtype).topN(a, B, n_top, **lists)
+            t2 = Restatement(dtype).topN(a, B, n_top, **lists)
+            assert t1[0] == t2[0] == 0 and np.array_equal(t1[2], t2[2])
+            diff = np.nonzero(t1[1] != t2[1])[0]                      # ids may differ only inside score ties
+            assert all((t1[2] == t1[2][j]).sum() > 1 for j in diff)
+
