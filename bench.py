@@ -58,6 +58,10 @@ def make_problem(cfg, dtype=np.float32):
 
 
 def team_name(code):
+    if code == 200:
+        return "lockstep"
+    if code >= 100:
+        return f"regtile{code - 100}w"
     return f"lanes{-code}" if code < 0 else ("block" if code == 1 else f"cluster{code}")
 
 

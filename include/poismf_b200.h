@@ -31,7 +31,10 @@ enum { PMF_SIDE_CSR = 0, PMF_SIDE_CSC = 1 };            /* CSR drives the A upda
 /* Numerics-mode flags (argument `flags`, or env POISMF_B200_FLAGS for the drop-in calls) */
 enum {
     PMF_FLAG_STRICT    = 1,  /* sequential sums, no FMA: mimics the reference built with naive BLAS */
-    PMF_FLAG_NO_CACHED = 2   /* cg: recompute every line-search objective from the factors        */
+    PMF_FLAG_NO_CACHED = 2,  /* cg: recompute every line-search objective from the factors        */
+    PMF_FLAG_NO_LOCKSTEP = 4 /* keep the heaviest rows on per-row teams: results then do not depend on how rows are
+                                sharded over GPUs (the lock-step path sums a heavy row's non-zeros in an order that
+                                depends on which other heavy rows the device holds; it is reproducible run to run) */
 };
 
 /* Hyper-parameters of a fit; same meaning as the arguments of run_poismf
@@ -104,7 +107,8 @@ int pmf_b200_ipc_import(pmf_b200_handle* h, int which, const void* handles, int 
  * for bench.py's roofline line: one entry per (side, row bin). */
 typedef struct pmf_b200_bin_profile {
     int side;                  /* PMF_SIDE_CSR / PMF_SIDE_CSC */
-    int block_team;            /* < 0: -lanes per row (sub-warp / warp teams); 1: CTA per row; > 1: CTAs per row (cluster) */
+    int block_team;            /* < 0: -lanes per row (sub-warp / warp teams); 1: CTA per row; 2..16: CTAs per row (cluster);
+                                  100 + w: register-tile kernel with w warps per row; 200: the heaviest rows, lock-step path */
     int cap;                   /* staged tile capacity (0: tile read from global memory) */
     int nrows;                 /* rows in the bin */
     unsigned long long nnz;    /* non-zeros in the bin */

@@ -11,6 +11,6 @@ Product surface:
 Nothing here falls back to the CPU: a missing library or a missing GPU raises.
 """
 from . import _lib  # noqa: F401
-from ._lib import FLAG_NO_CACHED, FLAG_STRICT, SIDE_CSC, SIDE_CSR, make_params  # noqa: F401
+from ._lib import FLAG_NO_CACHED, FLAG_NO_LOCKSTEP, FLAG_STRICT, SIDE_CSC, SIDE_CSR, make_params  # noqa: F401
 
-__all__ = ["c_funs", "device", "synth", "make_params", "FLAG_STRICT", "FLAG_NO_CACHED", "SIDE_CSR", "SIDE_CSC"]
+__all__ = ["c_funs", "device", "synth", "make_params", "FLAG_STRICT", "FLAG_NO_CACHED", "FLAG_NO_LOCKSTEP", "SIDE_CSR", "SIDE_CSC"]

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libpoismf_b200.so")
 PMF_F32, PMF_F64 = 0, 1
 METHODS = {"tncg": 1, "cg": 2, "pg": 3}
 SIDE_CSR, SIDE_CSC = 0, 1
-FLAG_STRICT, FLAG_NO_CACHED = 1, 2
+FLAG_STRICT, FLAG_NO_CACHED, FLAG_NO_LOCKSTEP = 1, 2, 4
 
 # every symbol include/poismf_b200.h declares (tests check that all are exported)
 SYMBOLS = [

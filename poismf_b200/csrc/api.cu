@@ -15,6 +15,7 @@
 #include <cstring>
 #include <cmath>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -28,6 +29,7 @@
 #include "ingest.cuh"
 #include "staged_copy.h"
 #include "kernels.cuh"
+#include "dense_rows.cuh"
 #include "launch.h"
 #include "topn_tc.cuh"
 
@@ -91,6 +93,7 @@ struct Bin {
     int cap = 0;            // staged tile capacity; 0 = tile stays in global memory
     int acap = -1;          // capacity of the per-non-zero arrays kept in shared memory (-1: == cap)
     int threads = 256;
+    int rt_nw = 0, rt_tpl = 0, rt_nc = 0;   // > 0: register-tile bin (regtile.cuh): warps per row, tile rows and chunks per lane
     size_t slice = 0, smem = 0;
     std::vector<int> rows;  // local row ids, longest first
     int* d_rows = nullptr;
@@ -99,7 +102,31 @@ struct Bin {
     std::vector<cudaEvent_t> ev;   // profiling: start/stop pairs of this bin's launches
 };
 
+// the heaviest rows of a side, solved in lock-step by the whole GPU (dense_rows.cuh)
+struct DensePlan {
+    int H = 0, T = 0, U = 256, nnzH = 0, nchunks = 0, G = 0;
+    unsigned long long nnz = 0;
+    std::vector<int> rows;                 // local row ids, heaviest first
+    void* blocks[20] = {};                 // every device allocation below, for release
+    int nblocks = 0;
+    int *hrow = nullptr, *hcol0 = nullptr, *seg_ptr = nullptr, *chunk_h = nullptr, *chunk_ptr = nullptr;
+    long long* hbeg = nullptr;
+    uint2* ent = nullptr;
+    float* sx = nullptr;
+    float *p = nullptr, *q = nullptr, *dvec = nullptr, *gprev = nullptr, *dprev = nullptr, *gpart = nullptr, *lsp = nullptr;
+    DenseScal* sc = nullptr;
+    std::vector<cudaEvent_t> ev;
+    void release()
+    {
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        for (int i = 0; i < nblocks; i++) dfree(blocks[i]);
+        nblocks = 0; H = 0; nnzH = 0; rows.clear(); nnz = 0;
+    }
+};
+
 template <class real> struct Side {
+    DensePlan dense;
     real* xv = nullptr;
     long long* ptr = nullptr;
     int* ind = nullptr;
@@ -118,6 +145,7 @@ template <class real> struct Side {
     void free_plan()
     {
         for (auto& b : bins) for (auto e : b.ev) cudaEventDestroy(e);
+        dense.release();
         if (d_all_rows) dfree(d_all_rows);
         if (gscratch) dfree(gscratch);
         d_all_rows = nullptr; gscratch = nullptr; d_empty = nullptr;
@@ -139,6 +167,7 @@ struct pmf_b200_handle {
     int k = 0, kp = 0, ldf = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    bool have_stream = false;   // `stream` is valid (the legacy default stream is the null handle: never test the value)
     int num_sms = 148;
     virtual ~pmf_b200_handle() {}
     virtual int set_matrix(int side, const void* values, const void* indptr, const void* indices, size_t nnz,
@@ -220,7 +249,7 @@ template <class real> struct HandleT : pmf_b200_handle {
     // wait for everything this handle has enqueued, then release the staging buffers
     int sync_all()
     {
-        cudaError_t e1 = stream ? cudaStreamSynchronize(stream) : cudaSuccess;
+        cudaError_t e1 = have_stream ? cudaStreamSynchronize(stream) : cudaSuccess;
         cudaError_t e2 = copy_stream ? cudaStreamSynchronize(copy_stream) : cudaSuccess;
         for (void* q : deferred) dfree(q);
         deferred.clear();
@@ -236,7 +265,7 @@ template <class real> struct HandleT : pmf_b200_handle {
         ldf = round_up(k, V);
         kp = tile_stride(k, V);
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        own_stream = true;
+        own_stream = true; have_stream = true;
         CK(dmalloc(&A, dimA * (size_t)ldf * sizeof(real)));
         ownA = true;
         CK(dmalloc(&B, dimB * (size_t)ldf * sizeof(real)));
@@ -376,10 +405,176 @@ template <class real> struct HandleT : pmf_b200_handle {
                    (size_t)4 * cap * sizeof(real) + (size_t)cap * kp * sizeof(real);
         return round_up_sz(b, 16);
     }
-    // row lists are uploaded on `st`; kernels that read them must be ordered after it
-    int plan(Side<real>& S, int method, bool strict, cudaStream_t st)
+    // ---- lock-step path for the heaviest rows (dense_rows.cuh) ------------------------------------
+    // returns 0: built, 1: error, 2: not applicable (sizes out of range)
+    std::vector<long long> dn_hbeg;
+    std::vector<int> dn_i32;
+    int build_dense(Side<real>& S, const std::vector<int>& hrows, size_t other, cudaStream_t st)
     {
-        const int key = method * 2 + (strict ? 1 : 0);
+        DensePlan& D = S.dense;
+        D.release();
+        const int H = (int)hrows.size();
+        int U = DN_TILE_ROWS;
+        if (const char* e = getenv("POISMF_B200_DENSE_TILE")) U = std::min(DN_TILE_ROWS, std::max(16, atoi(e)));   // tuning
+        const long long T = ((long long)other + U - 1) / U;
+        long long nnzH = 0;
+        for (int r : hrows) nnzH += S.h_ptr[r + 1] - S.h_ptr[r];
+        if (nnzH >= (1LL << 31) || T * H >= (1LL << 32) || S.nnz >= ((size_t)1 << 31)) return 2;
+        D.H = H; D.U = U; D.T = (int)T; D.nnzH = (int)nnzH; D.nnz = (unsigned long long)nnzH; D.rows = hrows;
+        D.G = (int)std::min<long long>(num_sms, T);         // persistent CTAs of the gaxpy pass
+        // host tables: [hrow H][hcol0 H+1][chunk_ptr H+1][chunk_h nchunks]
+        dn_hbeg.resize(H);
+        std::vector<int> hcol0(H + 1, 0), chunk_ptr(H + 1, 0);
+        for (int h = 0; h < H; h++) {
+            const long long n = S.h_ptr[hrows[h] + 1] - S.h_ptr[hrows[h]];
+            dn_hbeg[h] = S.h_ptr[hrows[h]];
+            hcol0[h + 1] = hcol0[h] + (int)n;
+            chunk_ptr[h + 1] = chunk_ptr[h] + (int)((n + DN_LS_CHUNK - 1) / DN_LS_CHUNK);
+        }
+        D.nchunks = chunk_ptr[H];
+        dn_i32.clear();
+        dn_i32.insert(dn_i32.end(), hrows.begin(), hrows.end());
+        dn_i32.insert(dn_i32.end(), hcol0.begin(), hcol0.end());
+        dn_i32.insert(dn_i32.end(), chunk_ptr.begin(), chunk_ptr.end());
+        for (int h = 0; h < H; h++)
+            for (int c = chunk_ptr[h]; c < chunk_ptr[h + 1]; c++) dn_i32.push_back(h);
+        auto grab = [&](auto** ptr, size_t bytes) -> int {
+            CK(dmalloc(ptr, std::max<size_t>(bytes, 16)));
+            D.blocks[D.nblocks++] = (void*)*ptr;
+            return 0;
+        };
+        int* tables = nullptr;
+        if (grab(&tables, dn_i32.size() * sizeof(int))) return 1;
+        D.hrow = tables; D.hcol0 = tables + H; D.chunk_ptr = D.hcol0 + H + 1; D.chunk_h = D.chunk_ptr + H + 1;
+        if (grab(&D.hbeg, (size_t)H * sizeof(long long))) return 1;
+        if (grab(&D.ent, (size_t)nnzH * sizeof(uint2))) return 1;
+        if (grab(&D.sx, (size_t)nnzH * sizeof(float))) return 1;
+        if (grab(&D.seg_ptr, ((size_t)T * H + 1) * sizeof(int))) return 1;
+        if (grab(&D.p, (size_t)nnzH * sizeof(float))) return 1;
+        if (grab(&D.q, (size_t)nnzH * sizeof(float))) return 1;
+        if (grab(&D.dvec, (size_t)H * ldf * sizeof(float))) return 1;
+        if (grab(&D.gprev, (size_t)H * 64 * sizeof(float))) return 1;
+        if (grab(&D.dprev, (size_t)H * 64 * sizeof(float))) return 1;
+        if (grab(&D.gpart, (size_t)D.G * H * ldf * sizeof(float))) return 1;
+        if (grab(&D.lsp, (size_t)D.nchunks * DN_TRIALS * sizeof(float))) return 1;
+        if (grab(&D.sc, (size_t)H * sizeof(DenseScal))) return 1;
+        CK(cudaMemcpyAsync(tables, dn_i32.data(), dn_i32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(D.hbeg, dn_hbeg.data(), (size_t)H * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(D.q, 0, (size_t)nnzH * sizeof(float), st));
+        // sort the heavy rows' non-zeros by (tile of the fixed matrix, heavy row); stable: ascending position inside
+        int *slot = nullptr, *pos = nullptr, *spos = nullptr;
+        unsigned *k1 = nullptr, *k2 = nullptr;
+        void* tmp = nullptr;
+        CK(dmalloc(&slot, (size_t)nnzH * sizeof(int))); deferred.push_back(slot);
+        CK(dmalloc(&pos, (size_t)nnzH * sizeof(int))); deferred.push_back(pos);
+        CK(dmalloc(&spos, (size_t)nnzH * sizeof(int))); deferred.push_back(spos);
+        CK(dmalloc(&k1, (size_t)nnzH * sizeof(unsigned))); deferred.push_back(k1);
+        CK(dmalloc(&k2, (size_t)nnzH * sizeof(unsigned))); deferred.push_back(k2);
+        int bits = 1;
+        while (bits < 32 && (1LL << bits) < T * H) bits++;
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k1, k2, pos, spos, (int)nnzH, 0, bits, st));
+        CK(dmalloc(&tmp, std::max<size_t>(tb, 16))); deferred.push_back(tmp);
+        const int grid = num_sms * 8;
+        dense_fill_slot_kernel<<<dim3(8, H), 256, 0, st>>>(D.hcol0, H, slot);
+        LAUNCHED();
+        dense_keys_kernel<<<grid, 256, 0, st>>>(S.ind, slot, D.hbeg, D.hcol0, (int)nnzH, H, U, k1, pos);
+        LAUNCHED();
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tb, k1, k2, pos, spos, (int)nnzH, 0, bits, st));
+        LAUNCHED();
+        dense_unpack_kernel<<<grid, 256, 0, st>>>(k2, spos, S.ind, (const float*)S.xv, D.hbeg, D.hcol0, (int)nnzH, H, U, ldf, D.ent, D.sx);
+        LAUNCHED();
+        dense_segments_kernel<<<grid, 256, 0, st>>>(k2, (int)nnzH, (int)(T * H), D.seg_ptr);
+        LAUNCHED();
+        CK(cudaGetLastError());
+        return 0;
+    }
+
+    // one half-sweep of the heavy rows: ~5 launches per cg iteration, all on `st`
+    int run_dense(Side<real>& S, real* M, const real* F, const HalfSweepConsts<real>& hc, int which_factor, cudaStream_t st)
+    {
+        return run_dense_impl(S, M, F, hc, which_factor, st);
+    }
+    int run_dense_impl(Side<float>& S, float* M, const float* F, const HalfSweepConsts<float>& hc, int which_factor,
+                       cudaStream_t st)
+    {
+        DensePlan& D = S.dense;
+        DenseParams P;
+        P.H = D.H; P.T = D.T; P.U = D.U; P.ldf = ldf; P.k = k; P.L = ldf / 4;
+        P.nnzH = D.nnzH; P.nchunks = D.nchunks; P.G = D.G;
+        P.R = (int)(which_factor == 0 ? dimB : dimA);
+        P.F = F; P.M = M + S.row_begin * (size_t)ldf; P.xv = S.xv; P.csum = csum;
+        P.hrow = D.hrow; P.hbeg = D.hbeg; P.hcol0 = D.hcol0; P.ent = D.ent; P.sx = D.sx;
+        P.seg_ptr = D.seg_ptr; P.chunk_h = D.chunk_h; P.chunk_ptr = D.chunk_ptr;
+        P.p = D.p; P.q = D.q; P.dvec = D.dvec; P.gprev = D.gprev; P.dprev = D.dprev; P.gpart = D.gpart; P.lsp = D.lsp;
+        P.sc = D.sc; P.hc = hc;
+        P.npeers = npeers[which_factor];
+        for (int q = 0; q < 7; q++)
+            P.peerM[q] = q < P.npeers ? peer[which_factor][q] + S.row_begin * (size_t)ldf : nullptr;
+        const size_t tile_bytes = (size_t)D.U * ldf * sizeof(float);
+        const size_t smem_dots = tile_bytes + (size_t)D.H * sizeof(int);
+        const size_t smem_g = 2 * tile_bytes + (size_t)(D.H + DN_GROUPS) * ldf * sizeof(float);
+        {
+            static std::mutex mu;
+            static std::map<int, std::pair<size_t, size_t>> done;      // per device: the attribute is a per-kernel maximum
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = done.find(device);
+            if (it == done.end() || it->second.first < smem_dots || it->second.second < smem_g) {
+                CK(cudaFuncSetAttribute(dense_walk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dots));
+                CK(cudaFuncSetAttribute(dense_walk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dots));
+                CK(cudaFuncSetAttribute(dense_walk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+                done[device] = std::make_pair(smem_dots, smem_g);
+            }
+        }
+        const int hg = (D.H + 3) / 4;
+        const int gd = (int)std::min<long long>(4 * num_sms, D.T);   // dots passes: four persistent CTAs per SM
+        dense_reset_kernel<<<(D.H + 127) / 128, 128, 0, st>>>(P);
+        dense_walk_kernel<0><<<gd, DnWalk<0>::threads, smem_dots, st>>>(P);
+        dense_ls_kernel<<<D.nchunks, 256, 0, st>>>(P, 0);
+        dense_init_kernel<<<hg, 128, 0, st>>>(P);
+        g_launches.fetch_add(4, std::memory_order_relaxed);
+        const long long maxiter = hc.maxupd <= 0 ? (1LL << 40) : hc.maxupd;
+        for (long long it = 0; it < maxiter; it++) {
+            dense_walk_kernel<2><<<D.G, DnWalk<2>::threads, smem_g, st>>>(P);
+            dense_k_kernel<<<D.H, 256, 0, st>>>(P);
+            dense_walk_kernel<1><<<gd, DnWalk<1>::threads, smem_dots, st>>>(P);
+            dense_ls_kernel<<<D.nchunks, 256, 0, st>>>(P, 1);
+            dense_choose_kernel<<<hg, 128, 0, st>>>(P);
+            g_launches.fetch_add(5, std::memory_order_relaxed);
+            if ((it & 7) == 7 && it + 1 < maxiter) {
+                // long iteration budgets (factors_multiple's cg): stop enqueueing once every row is done
+                std::vector<DenseScal> hs(D.H);
+                CK(cudaMemcpyAsync(hs.data(), D.sc, (size_t)D.H * sizeof(DenseScal), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                bool any = false;
+                for (auto& q : hs) any = any || q.active;
+                if (!any) break;
+            }
+        }
+        CK(cudaGetLastError());
+        return 0;
+    }
+    int run_dense_impl(Side<double>&, double*, const double*, const HalfSweepConsts<double>&, int, cudaStream_t)
+    {
+        return fail("lock-step path is float32 only");
+    }
+
+    // Register-tile kernels (regtile.cuh) take the rows of up to 512 non-zeros when the fit is float32 in
+    // fast numerics with w_mult == 1 and k <= 64: pg, and cg with limit_step and the cached line search.
+    bool regtile_ok(const pmf_b200_params& p) const
+    {
+        if (!std::is_same<real, float>::value || (p.flags & PMF_FLAG_STRICT) || (real)p.w_mult != (real)1) return false;
+        if (ldf > 64 || getenv("POISMF_B200_NO_REGTILE")) return false;
+        if (p.method == PMF_PG) return true;
+        return p.method == PMF_CG && p.limit_step && !(p.flags & PMF_FLAG_NO_CACHED);
+    }
+    // row lists are uploaded on `st`; kernels that read them must be ordered after it
+    int plan(Side<real>& S, const pmf_b200_params& p, cudaStream_t st)
+    {
+        const int method = p.method;
+        const bool strict = (p.flags & PMF_FLAG_STRICT) != 0;
+        const bool rt = regtile_ok(p);
+        const int key = method * 8 + (strict ? 1 : 0) + (rt ? 2 : 0) + ((p.flags & PMF_FLAG_NO_LOCKSTEP) ? 4 : 0);
         if (S.planned_method == key) return 0;
         if (S.planned_method >= 0) {    // re-planning for another method: the old lists may be in use
             if (sync_all()) return 1;
@@ -407,6 +602,18 @@ template <class real> struct HandleT : pmf_b200_handle {
                 q += used;
                 if (*q == ',') q++;
             }
+        }
+        if (rt) {
+            // register-tile bins: {warps per row, tile rows per lane}; capacity 8 x warps x tile rows
+            static const int rdef[11][2] = {{1, 2}, {1, 3}, {1, 4}, {2, 3}, {2, 4}, {4, 3}, {4, 4}, {8, 3}, {8, 4}, {16, 3}, {16, 4}};
+            for (int c = 0; c < 11; c++) {
+                Bin b;
+                b.block = true; b.rt_nw = rdef[c][0]; b.rt_tpl = rdef[c][1]; b.rt_nc = ldf <= 32 ? 2 : 4;
+                b.cap = 8 * b.rt_nw * b.rt_tpl; b.threads = 32 * b.rt_nw;
+                b.width = b.threads;
+                bins.push_back(b);
+            }
+            nw = 0;     // the shared-memory (sub-)warp teams are not used
         }
         for (int c = 0; c < nw; c++) {
             const int width = wdef[c][0];
@@ -490,11 +697,39 @@ template <class real> struct HandleT : pmf_b200_handle {
             b.smem = b.slice;
             bins.push_back(b);
         }
+        // the heaviest rows go to the lock-step path (dense_rows.cuh): cg under the register-tile conditions
+        std::vector<char> is_dense;
+        if (rt && method == PMF_CG && !(p.flags & PMF_FLAG_NO_LOCKSTEP) && !getenv("POISMF_B200_NO_DENSE")) {
+            long long dmin = 4096;
+            if (const char* e = getenv("POISMF_B200_DENSE_MIN")) dmin = std::max(1LL, atoll(e));
+            // shared memory of the gaxpy pass: two tiles of 256 rows + one accumulator row per heavy row
+            // (+ the per-group edge slots)
+            const size_t hmax = std::min<size_t>(1024, (SMEM_CTA_MAX - 1024) / ((size_t)ldf * sizeof(real)) - 2 * DN_TILE_ROWS - DN_GROUPS);
+            std::vector<std::pair<long long, int>> cand;
+            for (size_t r = 0; r < S.n_rows; r++) {
+                const long long n = S.h_ptr[r + 1] - S.h_ptr[r];
+                if (n >= dmin) cand.push_back({-n, (int)r});
+            }
+            std::sort(cand.begin(), cand.end());          // heaviest first, ties by row id
+            if (cand.size() > hmax) cand.resize(hmax);
+            if (!cand.empty()) {
+                std::vector<int> hrows;
+                for (auto& c : cand) hrows.push_back(c.second);
+                const size_t other = (&S == &sides[0]) ? dimB : dimA;
+                const int rc = build_dense(S, hrows, other, st);
+                if (rc == 1) return 1;
+                if (rc == 0) {
+                    is_dense.assign(S.n_rows, 0);
+                    for (int r : hrows) is_dense[r] = 1;
+                }
+            }
+        }
         std::vector<int>& empty = S.h_empty;
         empty.clear();
         for (size_t r = 0; r < S.n_rows; r++) {
             const long long n = S.h_ptr[r + 1] - S.h_ptr[r];
             if (n == 0) { empty.push_back((int)r); continue; }
+            if (!is_dense.empty() && is_dense[r]) continue;
             size_t bi = 0;
             while (bi + 1 < bins.size() && n > (long long)bins[bi].cap * bins[bi].cluster) bi++;
             bins[bi].rows.push_back((int)r);
@@ -569,6 +804,12 @@ template <class real> struct HandleT : pmf_b200_handle {
         return 0;
     }
 
+    static cudaError_t launch_regtile(const LaunchCfg& cfg, const SideParams<float>& P)
+    {
+        return P.hc.method == M_PG ? launch_regtile_pg(cfg, P) : launch_regtile_cg(cfg, P);
+    }
+    static cudaError_t launch_regtile(const LaunchCfg&, const SideParams<double>&) { return cudaErrorInvalidConfiguration; }
+
     // ---- one half-sweep ----------------------------------------------------------
     // side CSC: update local rows of B with A fixed (src/poismf.c:510-557)
     // side CSR: update local rows of A with B fixed (:561-604)
@@ -588,7 +829,7 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (!S.ptr) return fail("half_sweep: matrix for side %d not set", side);
         if (p.method != PMF_PG && p.method != PMF_CG && p.method != PMF_TNCG) return fail("bad method");
         const bool strict = (p.flags & PMF_FLAG_STRICT) != 0;
-        if (plan(S, p.method, strict, stream)) return 1;
+        if (plan(S, p, stream)) return 1;
         const bool updA = side == PMF_SIDE_CSR;
         real* M = updA ? A : B;
         const real* F = updA ? B : A;
@@ -637,6 +878,14 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (overlap) CK(cudaEventRecord(ev_fork, stream));
         int n_launched = 0;
         bool used[NAUX] = {};
+        if (S.dense.H > 0) {                                      // the heaviest rows: lock-step path, own stream
+            cudaStream_t ls = stream;
+            if (overlap) { ls = aux[0]; CK(cudaStreamWaitEvent(ls, ev_fork, 0)); used[0] = true; n_launched = 1; }
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profiling) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, stream)); }
+            if (run_dense(S, M, F, hc, updA ? 0 : 1, ls)) return 1;
+            if (profiling) { CK(cudaEventRecord(ev1, stream)); S.dense.ev.push_back(ev0); S.dense.ev.push_back(ev1); }
+        }
         for (int bi = (int)S.bins.size() - 1; bi >= 0; bi--) {    // heaviest rows first
             const Bin& b = S.bins[bi];
             if (b.rows.empty()) continue;
@@ -678,13 +927,16 @@ template <class real> struct HandleT : pmf_b200_handle {
             cfg.max_grid = b.cap == 0 ? S.gs_ctas / b.cluster : (1 << 30);
             cfg.num_sms = num_sms;
             cfg.cluster = b.cluster;
+            cfg.rt_nw = b.rt_nw; cfg.rt_tpl = b.rt_tpl; cfg.rt_nc = b.rt_nc;
             cudaError_t e;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) {
                 CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
                 CK(cudaEventRecord(ev0, stream));
             }
-            if (b.cluster > 1)
+            if (b.rt_nw > 0)
+                e = launch_regtile(cfg, P);
+            else if (b.cluster > 1)
                 e = p.method == PMF_TNCG ? launch_gang_tn_fast<real>(cfg, P) : launch_gang_pgcg_fast<real>(cfg, P);
             else if (p.method == PMF_TNCG)
                 e = strict ? launch_rows_tn_strict<real>(cfg, P) : launch_rows_tn_fast<real>(cfg, P);
@@ -743,22 +995,37 @@ template <class real> struct HandleT : pmf_b200_handle {
 
     void clear_profile() override
     {
-        for (int sd = 0; sd < 2; sd++)
+        for (int sd = 0; sd < 2; sd++) {
             for (auto& b : sides[sd].bins) {
                 for (auto e : b.ev) cudaEventDestroy(e);
                 b.ev.clear();
             }
+            for (auto e : sides[sd].dense.ev) cudaEventDestroy(e);
+            sides[sd].dense.ev.clear();
+        }
     }
     int get_profile(pmf_b200_bin_profile* out, int max_entries) override
     {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         int n = 0;
+        for (int sd = 0; sd < 2; sd++) {
+            DensePlan& D = sides[sd].dense;
+            if (D.H > 0 && n < max_entries) {
+                pmf_b200_bin_profile& o = out[n++];
+                o.side = sd; o.block_team = 200; o.cap = 0; o.nrows = D.H; o.nnz = D.nnz; o.launches = D.ev.size() / 2; o.ms = 0;
+                for (size_t i = 0; i + 1 < D.ev.size(); i += 2) {
+                    float ms = 0;
+                    if (cudaEventElapsedTime(&ms, D.ev[i], D.ev[i + 1]) == cudaSuccess) o.ms += ms;
+                }
+            }
+        }
         for (int sd = 0; sd < 2; sd++)
             for (auto& b : sides[sd].bins) {
                 if (b.rows.empty() || n >= max_entries) continue;
                 pmf_b200_bin_profile& o = out[n++];
-                o.side = sd; o.block_team = b.block ? b.cluster : -b.width; o.cap = b.cap; o.nrows = (int)b.rows.size();
+                o.side = sd; o.block_team = b.rt_nw > 0 ? 100 + b.rt_nw : (b.block ? b.cluster : -b.width);
+                o.cap = b.cap; o.nrows = (int)b.rows.size();
                 o.nnz = b.nnz; o.launches = b.ev.size() / 2; o.ms = 0;
                 for (size_t i = 0; i + 1 < b.ev.size(); i += 2) {
                     float ms = 0;
@@ -978,7 +1245,7 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (copy_in(B, Bh, dimB, stream)) return 1;
         if (!matrix_resident &&
             upload_matrix(PMF_SIDE_CSC, Xc, Xc_indptr, Xc_indices, nnz_c, index_bytes, 0, dimB, stream)) return 1;
-        if (plan(sides[PMF_SIDE_CSC], p.method, strict, stream)) return 1;
+        if (plan(sides[PMF_SIDE_CSC], p, stream)) return 1;
         if (timing) { if (sync_all()) return 1; lap("up A,B,CSC+plan"); }
         bool csr_up = false, b_down = false;
         SweepHooks hk;
@@ -986,7 +1253,7 @@ template <class real> struct HandleT : pmf_b200_handle {
             csr_up = true;
             if (!matrix_resident &&
                 upload_matrix(PMF_SIDE_CSR, Xr, Xr_indptr, Xr_indices, nnz_r, index_bytes, 0, dimA, copy_stream)) return 1;
-            if (plan(sides[PMF_SIDE_CSR], p.method, strict, copy_stream)) return 1;
+            if (plan(sides[PMF_SIDE_CSR], p, copy_stream)) return 1;
             CK(cudaEventRecord(ev_copy, copy_stream));
             CK(cudaStreamWaitEvent(stream, ev_copy, 0));
             if (timing) { cudaStreamSynchronize(copy_stream); lap("up CSR+plan"); cudaStreamSynchronize(stream); lap("B half-sweep"); }
@@ -1050,9 +1317,11 @@ extern "C" int pmf_b200_bind_factors(pmf_b200_handle* h, void* A, void* B) { ret
 extern "C" void* pmf_b200_factor_ptr(pmf_b200_handle* h, int which) { return h->factor_ptr(which); }
 extern "C" int pmf_b200_set_stream(pmf_b200_handle* h, void* s)
 {
-    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaSetDevice(h->device);
+    if (h->have_stream) cudaStreamSynchronize(h->stream);      // work enqueued so far stays ordered before the switch
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     h->stream = (cudaStream_t)s;
-    h->own_stream = false;
+    h->own_stream = false; h->have_stream = true;
     return 0;
 }
 extern "C" int pmf_b200_sweeps(pmf_b200_handle* h, const pmf_b200_params* p) { return h->sweeps(*p); }

@@ -16,15 +16,23 @@ namespace pmf {
 // than there are rows to hand out.
 // occupancy queries (and the attribute calls that go with them) are cached per
 // (kernel, block size, shared bytes, cluster size): they cost far more than a launch
+// Function attributes and occupancy are PER DEVICE: both caches carry the current device id (a
+// process may hold handles on several GPUs: pmf_b200_create(device), POISMF_B200_DEVICE).
 static std::mutex g_occ_mutex;
-static std::map<std::tuple<const void*, int, size_t, int>, int> g_occ_cache;
+static std::map<std::tuple<int, const void*, int, size_t, int>, int> g_occ_cache;
+static inline int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
 
 template <class K> static int persistent_grid(K kern, const LaunchCfg& cfg)
 {
     int occ = 1;
     {
         std::lock_guard<std::mutex> lk(g_occ_mutex);
-        auto key = std::make_tuple((const void*)kern, cfg.threads, cfg.smem_bytes, 1);
+        auto key = std::make_tuple(current_device(), (const void*)kern, cfg.threads, cfg.smem_bytes, 1);
         auto it = g_occ_cache.find(key);
         if (it != g_occ_cache.end()) occ = it->second;
         else {
@@ -43,12 +51,13 @@ template <class K> static int persistent_grid(K kern, const LaunchCfg& cfg)
 // it is only ever raised (bins of different tile capacity share one kernel)
 template <class K> static cudaError_t ensure_smem(K kern, size_t bytes)
 {
-    static std::map<const void*, size_t> current;
+    static std::map<std::pair<int, const void*>, size_t> current;
     std::lock_guard<std::mutex> lk(g_occ_mutex);
-    auto it = current.find((const void*)kern);
+    const auto key = std::make_pair(current_device(), (const void*)kern);
+    auto it = current.find(key);
     if (it != current.end() && it->second >= bytes) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) current[(const void*)kern] = bytes;
+    if (e == cudaSuccess) current[key] = bytes;
     return e;
 }
 
@@ -114,7 +123,7 @@ static cudaError_t launch_gang_thr(const LaunchCfg& cfg, const SideParams<real>&
     int nclusters = 0;
     {
         std::lock_guard<std::mutex> lk(g_occ_mutex);
-        auto key = std::make_tuple((const void*)kern, cfg.threads, cfg.smem_bytes, cfg.cluster);
+        auto key = std::make_tuple(current_device(), (const void*)kern, cfg.threads, cfg.smem_bytes, cfg.cluster);
         auto it = g_occ_cache.find(key);
         if (it != g_occ_cache.end()) nclusters = it->second;
         else {

@@ -133,3 +133,27 @@ def fm_hyper(case, k):
     if kw.get("maxupd", 0) is None:
         kw["maxupd"] = 15 * k
     return method, kw
+
+
+# ---- per-row objective of the cg sub-problem, in float64 (calc_fun_single, src/poismf.c:194-208) ----
+def row_objectives(M, F, mat, l2, w=1.0, l1=0.0, with_l2=True, chunk=1 << 22):
+    """f_i = <colsum(F)+l1, m_i> + l2 |m_i|^2 - w * sum_j x_ij log <m_i, F_j> for every row i of the
+    compressed matrix `mat` = (values, indptr, indices); rows without non-zeros get the regulariser only.
+    `with_l2=False` gives tncg's objective (quirk Q3).  Rows whose prediction is <= 0 get +inf."""
+    vals, ptr, ind = mat
+    ptr = ptr.astype(np.int64)
+    M64 = M.astype(np.float64)
+    csum = F.sum(axis=0, dtype=np.float64) + l1
+    f = M64 @ csum
+    if with_l2:
+        f += l2 * np.einsum("ij,ij->i", M64, M64)
+    rows = np.repeat(np.arange(M.shape[0]), np.diff(ptr))
+    ls = np.zeros(M.shape[0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for s in range(0, rows.shape[0], chunk):
+            sl = slice(s, s + chunk)
+            p = np.einsum("ij,ij->i", M64[rows[sl]], F[ind[sl].astype(np.int64)].astype(np.float64))
+            t = vals[sl].astype(np.float64) * np.log(p)
+            t[~(p > 0)] = -np.inf
+            ls += np.bincount(rows[sl], weights=t, minlength=M.shape[0])
+    return f - w * ls
