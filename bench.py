@@ -1,26 +1,33 @@
 #!/usr/bin/env python
 """bench.py — poismf_b200 headline benchmark.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|small|c1|c3s|c3|c4s|c5s]
 
 Metric (BASELINE.json): nnz processed per second per alternating sweep.
-A "step" is ONE alternating sweep (B half-sweep over CSC + A half-sweep over CSR) of the
-workload; at N=1 the workload is BASELINE config #2 — Last.FM-360K-shaped synthetic,
-359k users x 160k items, 17.5M power-law draws, k=50, method=cg (maxupd 5, l2 1e4,
-limit_step), float32 (the reference's Python default, poismf/__init__.py:240).
+A "step" is ONE alternating sweep (B half-sweep over CSC + A half-sweep over CSR) of the workload; at
+N=1 the workload is BASELINE config #2 — Last.FM-360K-shaped synthetic, 359k users x 160k items, 17.5M
+power-law draws, k=50, method=cg (maxupd 5, l2 1e4, limit_step), float32 (the reference's Python default,
+poismf/__init__.py:240).  Other configs (not the driver's bench line): c3s / c3 Netflix-shaped tncg k=100,
+c4s web-scale-shaped pg k=64 (1/10 scale in users, items and non-zeros), c5s batched topN (users/s).
 
-  value    : nnz / device time per sweep, inputs resident in HBM (CUDA events on the
-             launching stream, max over ranks); the K timed steps are sweeps 1..K of one fit
-  e2e      : the same metric through the drop-in C ABI call run_poismf (numiter=1) with HOST
+  value    : nnz / device time per sweep, inputs resident in HBM (CUDA events on the launching stream, max
+             over ranks); the K timed steps are sweeps 1..K of ONE fit from the initial factors
+  e2e      : the same metric through the drop-in C ABI call run_poismf (numiter=1) with page-locked HOST
              buffers: H2D of CSR+CSC+factors and D2H of the factors inside the timed region
-  roofline : dominant row-kernel bin: algorithmic bytes of the bin / its average launch time
-  cpu_baseline : the reference's own C path (oracle/_ref, OpenMP, all host cores) on a bounded sample
+             (`e2e_pageable`: the same call on ordinary pageable numpy arrays, what the reference's callers pass)
+  roofline : dominant launch of the sweep: algorithmic bytes of its rows / its average device time
+  cpu_baseline : the reference's own C path (oracle/_ref, OpenMP, all host cores) on the SAME arrays, sweeps
+             1..3 of one fit
+  parity   : (N > 1) after the timed region every rank hashes its replicas and rank 0 repeats the sweeps
+             on one GPU
 
---impl reference times only the reference's CPU implementation (rank 0; other ranks exit).
+--impl reference times only the reference's CPU implementation on the same arrays, sweeps 1..K of one fit
+(rank 0; other ranks exit).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -44,7 +51,20 @@ CONFIGS = {
     "c1": dict(dimA=100, dimB=1000, nnz=10_000, k=5, method="pg",
                hp=dict(l2_reg=1e9, maxupd=1, step_size=1e-7),
                label="README synthetic 100 x 1000, 1e4 nnz, k=5, pg"),
+    # BASELINE config #3 (Netflix-shaped, tncg, k=100, maxupd = 15 k): full size and 1/10 of the users
+    "c3": dict(dimA=480_000, dimB=17_700, nnz=100_000_000, k=100, method="tncg",
+               hp=dict(l2_reg=1e3, maxupd=1500), alpha=(0.5, 0.7),
+               label="netflix-shaped synthetic 480k x 17.7k, 100M power-law draws, k=100, tncg"),
+    "c3s": dict(dimA=48_000, dimB=17_700, nnz=10_000_000, k=100, method="tncg",
+                hp=dict(l2_reg=1e3, maxupd=1500), alpha=(0.5, 0.7),
+                label="1/10-scale netflix-shaped synthetic 48k x 17.7k, 10M power-law draws, k=100, tncg"),
+    # BASELINE config #4 (web-scale, pg, k=64, maxupd 1) at 1/10 of the users, items and non-zeros
+    "c4s": dict(dimA=1_000_000, dimB=100_000, nnz=200_000_000, k=64, method="pg",
+                hp=dict(l2_reg=1e9, maxupd=1, step_size=1e-7),
+                label="1/10-scale web-scale synthetic 1M x 100k, 200M power-law draws, k=64, pg"),
 }
+TOPN = dict(users=32_768, items=1_000_000, k=64, top_n=100, excl=200,
+            label="batched topN: 32k users x 1M items, k=64, top-100, ~200 excluded items per user")
 
 
 def make_problem(cfg, dtype=np.float32):
@@ -52,7 +72,8 @@ def make_problem(cfg, dtype=np.float32):
     if cfg["dimA"] == 100:
         csr, csc = readme_counts(dtype=dtype)
     else:
-        csr, csc = powerlaw_counts(cfg["dimA"], cfg["dimB"], cfg["nnz"], dtype=dtype, seed=1)
+        aa, ab = cfg.get("alpha", (0.6, 0.9))
+        csr, csc = powerlaw_counts(cfg["dimA"], cfg["dimB"], cfg["nnz"], alpha_a=aa, alpha_b=ab, dtype=dtype, seed=1)
     A0, B0 = init_factors(cfg["dimA"], cfg["dimB"], cfg["k"], seed=1, dtype=dtype)
     return csr, csc, A0, B0
 
@@ -119,31 +140,104 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_reference(cfg, steps, warmup, fast=True):
-    """The reference's own CPU path (oracle/_ref) on a bounded sample; returns (nnz/s, info)."""
+def run_reference(cfg, problem, sweeps, warmup_sweeps=0):
+    """The reference's own CPU path (oracle/_ref, -O3 OpenMP build of /root/reference/src) on the SAME arrays
+    as the device arm: sweeps 1..`sweeps` of ONE fit from the initial factors (what the device arm times).
+    Returns (ms per sweep, info)."""
     from oracle.oracle import Ref, Restatement
-    sample_cfg = CONFIGS["small"] if cfg["dimA"] > 50_000 else cfg
-    csr, csc, A0, B0 = make_problem(sample_cfg)
+    csr, csc, A0, B0 = problem
     nnz = int(csr[0].shape[0])
     cores = os.cpu_count() or 1
-    if Ref.available(np.float32, fast=fast):
-        lib, kind = Ref(np.float32, fast=fast), "reference"
+    if Ref.available(np.float32, fast=True):
+        lib, kind = Ref(np.float32, fast=True), "reference"
     else:
         lib, kind, cores = Restatement(np.float32), "port", 1
-    hp = dict(sample_cfg["hp"])
-    times = []
-    for it in range(warmup + steps):
+    hp = dict(cfg["hp"])
+    if warmup_sweeps:
         A, B = A0.copy(), B0.copy()
+        lib.run_poismf(A, B, csr, csc, cfg["method"], numiter=warmup_sweeps, nthreads=cores, **hp)
+    A, B = A0.copy(), B0.copy()
+    t0 = time.perf_counter()
+    lib.run_poismf(A, B, csr, csc, cfg["method"], numiter=sweeps, nthreads=cores, **hp)
+    ms = 1e3 * (time.perf_counter() - t0) / sweeps
+    build = ("-O3 x86-64-v3 OpenMP build of /root/reference/src + sequential BLAS" if kind == "reference"
+             else "scalar restatement")
+    info = {"value": nnz / (ms / 1e3), "unit": "nnz/s per sweep", "cores": cores, "kind": kind, "same_config": True,
+            "sample": f"the full workload ({cfg['label']}: {nnz} stored nnz), sweeps 1..{sweeps} of one fit from the "
+                      f"initial factors ({build})"}
+    return ms, info
+
+
+def topn_problem():
+    rng = np.random.default_rng(5)
+    t = TOPN
+    A = np.ascontiguousarray(rng.gamma(0.5, 0.5, size=(t["users"], t["k"])).astype(np.float32))
+    B = np.ascontiguousarray(rng.gamma(0.5, 0.5, size=(t["items"], t["k"])).astype(np.float32))
+    lens = rng.poisson(t["excl"], t["users"])
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    eix = rng.integers(0, t["items"], int(ptr[-1])).astype(np.uint64)
+    return A, B, ptr, eix
+
+
+def bench_topn(args, rank, world, local_rank):
+    """c5s: users ranked per second through the batched topN entry (host buffers in and out: an e2e figure)."""
+    import torch
+    from poismf_b200 import _lib, c_funs
+    from poismf_b200.sharding import user_ranges
+    _lib.require_gpu()
+    torch.cuda.set_device(local_rank)
+    os.environ["POISMF_B200_DEVICE"] = str(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t = TOPN
+    A, B, ptr, eix = topn_problem()
+    lo, hi = user_ranges(t["users"], world)[rank]
+    users = np.arange(lo, hi, dtype=np.uint64)
+    p64 = ptr.astype(np.int64)
+    lptr = (p64[lo:hi + 1] - p64[lo]).astype(np.uint64)
+    leix = np.ascontiguousarray(eix[p64[lo]:p64[hi]])
+
+    def one():
         t0 = time.perf_counter()
-        lib.run_poismf(A, B, csr, csc, sample_cfg["method"], numiter=1, nthreads=cores, **hp)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
-    info = {"value": nnz / (ms / 1e3), "unit": "nnz/s per sweep", "cores": cores, "kind": kind,
-            "sample": f"{sample_cfg['label']}: {nnz} nnz, 1 sweep from init per step, {steps} steps"
-                      f" ({'-O3 x86-64-v3 OpenMP build of /root/reference/src + naive BLAS' if kind == 'reference' else 'scalar restatement'})"}
-    return ms, nnz, info
+        c_funs._topN_batch(A, B, users=users, excl_ptr=lptr, excl_ix=leix, top_n=t["top_n"], output_score=True)
+        return time.perf_counter() - t0
+    for _ in range(max(args.warmup, 1)):
+        one()
+    _lib.topn_stats(reset=True)
+    if dist is not None:
+        dist.barrier()
+    ts = [one() for _ in range(args.steps)]
+    n_tc, n_redo = _lib.topn_stats(reset=True)
+    ms = 1e3 * float(np.mean(ts))
+    if dist is not None:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        # dense tf32 peak: half the measured bf16 cuBLAS figure (B200_PROFILING.md: 1.1 vs 2.25 PF nominal)
+        peak = float(peaks.get("bf16_tflops", 1590.0)) / 2
+        flops = 2.0 * t["users"] * t["items"] * t["k"] * 2          # two scoring passes (threshold, candidates)
+        line = {"metric": "users ranked/sec (batched topN)", "value": t["users"] / (ms / 1e3), "unit": "users/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "tf32 candidates + f32 exact re-score", "data": "synthetic",
+                "config": {"workload": t["label"], "parallelism": f"users sharded x{args.gpus}, B replicated"},
+                "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                             "frac": flops / (ms / 1e3) / 1e12 / peak, "traffic": None,
+                             "note": "end-to-end call (upload of A, B and the exclusion lists, two TF32 scoring passes, exact "
+                                     "re-score, download) against half the measured bf16 cuBLAS peak"},
+                "topn_users_on_tensor_cores": int(n_tc), "topn_users_redone_exactly": int(n_redo)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
 
 
 def main():
@@ -152,40 +246,52 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c5s"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: refresh replicas by peer-memory stores from the row kernels (p2p) or NCCL broadcasts")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-host", "nccl"],
+                    help="N>1: refresh replicas by peer-memory stores from the row kernels, completion signalled on the "
+                         "device (p2p) or by a host barrier (p2p-host), or by NCCL broadcasts")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config == "c5s":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "c5s: the reference has no batched topN entry point"}))
+            return 0
+        return bench_topn(args, rank, world, local_rank)
+    cfg = CONFIGS[args.config]
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    xdesc = {"p2p": "NVLink peer-memory stores fused into the row kernels, completion signalled on the device",
+             "p2p-host": "NVLink peer-memory stores fused into the row kernels + host barrier",
+             "nccl": "NCCL broadcasts"}[args.exchange]
     config_line = {"workload": cfg["label"], "method": cfg["method"], "k": cfg["k"], **cfg["hp"],
-                   "l2_flush": "inputs larger than L2 (factors+CSR+CSC ~0.5 GB vs 126 MB)",
-                   "parallelism": (f"rows/cols sharded x{args.gpus}, replicas refreshed by "
-                                   f"{'NVLink peer-memory stores fused into the row kernels' if args.exchange == 'p2p' else 'NCCL broadcasts'}")
-                   if args.gpus > 1 else "single GPU"}
+                   "l2_flush": "inputs larger than L2 (factors+CSR+CSC vs 126 MB)",
+                   "parallelism": f"rows/cols sharded x{args.gpus}, replicas refreshed by {xdesc}" if args.gpus > 1 else "single GPU"}
+    metric = "nnz processed/sec per alternating sweep"
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ms, nnz, info = run_reference(cfg, args.steps, args.warmup)
-        line = {"impl": "reference", "metric": "nnz processed/sec per alternating sweep", "value": info["value"],
+        problem = make_problem(cfg)
+        ms, info = run_reference(cfg, problem, args.steps, warmup_sweeps=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": metric, "value": info["value"],
                 "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config_line, "cpu_baseline": info,
+                "dtype": "f32", "data": "synthetic", "config": config_line, "nnz": int(problem[0][0].shape[0]),
+                "cpu_baseline": info,
                 "e2e": {"value": info["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ our arm
     import torch
-    from poismf_b200 import _lib, c_funs, make_params
+    from poismf_b200 import FLAG_NO_LOCKSTEP, _lib, c_funs, make_params
     from poismf_b200.device import DeviceFit
     _lib.require_gpu()
     torch.cuda.set_device(local_rank)
@@ -194,10 +300,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = _lib.lib()
-    csr, csc, A0, B0 = make_problem(cfg)
+    problem = make_problem(cfg)
+    csr, csc, A0, B0 = problem
     nnz = int(csr[0].shape[0])
     dimA, dimB, k = cfg["dimA"], cfg["dimB"], cfg["k"]
     params = make_params(cfg["method"], numiter=1, flags=args.flags, **cfg["hp"])
+    be = None
 
     if world == 1:
         fit = DeviceFit(dimA, dimB, k, np.float32, device=local_rank)
@@ -206,6 +314,7 @@ def main():
         fit.set_csr_csc(csr, csc)
         reset = lambda: fit.set_factors(A0, B0)
         sweep = lambda: fit.sweeps(params)
+        finish = lambda: None
         profiler = fit
     else:
         from poismf_b200.sharding import GpuBackend, ShardedSweep
@@ -214,9 +323,11 @@ def main():
         drv = ShardedSweep(be, dimA, dimB, np.float32)
         reset = lambda: be.reset(A0, B0)
         sweep = lambda: drv.run(params)
+        finish = be.finish
         profiler = be.fit
 
     def barrier():
+        finish()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -264,7 +375,7 @@ def main():
     ms_step = ms_total / args.steps
     value = nnz / (ms_step / 1e3)
 
-    # roofline of the dominant row-kernel bin (by device time), rank 0's shard
+    # roofline of the dominant launch (by device time), rank 0's shard
     roof = None
     if prof:
         peaks = {}
@@ -276,8 +387,7 @@ def main():
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         top = max(prof, key=lambda p: p["ms"])
         s = 4
-        other = dimB if top["side"] == 0 else dimA
-        # the opposite factor matrix's column-sum read is a separate kernel: not charged to the bin
+        # the opposite factor matrix's column-sum read is a separate kernel: not charged to the launch
         bytes_launch = top["nnz"] * (k * s + s + 4) + top["nrows"] * (2 * k * s + 8)
         avg_ms = top["ms"] / max(top["launches"], 1)
         achieved = bytes_launch / (avg_ms / 1e3) / 1e9 if avg_ms > 0 else 0.0
@@ -285,42 +395,74 @@ def main():
         traffic = None
         try:   # DRAM bytes of this launch from the committed ncu --set full capture of the same command
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get(f"side{top['side']}_{team_name(top['block_team'])}_cap{top['cap']}")
+            traffic = tj.get(f"{args.config}_side{top['side']}_{team_name(top['block_team'])}_cap{top['cap']}")
         except Exception:
             pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": which,
-                "kernel": f"rows_{team_name(top['block_team'])}_kernel<{cfg['method']}> side="
+                "kernel": f"{team_name(top['block_team'])}<{cfg['method']}> side="
                           f"{'CSR(A)' if top['side'] == 0 else 'CSC(B)'} cap={top['cap']} rows={top['nrows']} nnz={top['nnz']}",
                 "kernel_avg_ms": avg_ms, "kernel_share_of_step": top["ms"] / max(ms_profiled_pass, 1e-9),
                 "serialized_ms_per_step": ms_profiled_pass / args.steps,
                 "sweep_algorithmic_GBps": sweep_bytes / (ms_step / 1e3) / 1e9,
                 "sweep_frac_of_peak": sweep_bytes / (ms_step / 1e3) / 1e9 / peak,
                 "bins": [{"side": p["side"], "team": team_name(p["block_team"]), "cap": p["cap"],
-                          "rows": p["nrows"], "nnz": p["nnz"], "ms_per_sweep": p["ms"] / args.steps} for p in prof]}
-        # the solver re-reads every staged tile once per evaluation pass, out of shared memory
-        # (or L2 for streamed rows); upper bound of passes per row and the on-chip traffic that implies
+                          "rows": p["nrows"], "nnz": p["nnz"], "ms_per_sweep": p["ms"] / args.steps,
+                          "GBps": (p["nnz"] * (k * s + s + 4) + p["nrows"] * (2 * k * s + 8)) / max(p["ms"] / args.steps, 1e-9) / 1e6}
+                         for p in prof]}
+        # the solver re-reads every tile once per evaluation pass, out of registers / shared memory
         mu = int(cfg["hp"].get("maxupd", 1))
         passes = {"cg": 1 + 2 * mu, "pg": 2 * mu}.get(cfg["method"])
         if passes:
             roof["tile_passes_per_row_max"] = passes
             roof["onchip_tile_GBps_upper"] = 2 * nnz * k * s * passes / (ms_step / 1e3) / 1e9
 
-    # e2e: drop-in run_poismf with host buffers (rank 0 alone at N=1; sharded path otherwise reuses value)
-    e2e = None
+    # ---- N > 1: every rank hashes its replicas; rank 0 repeats the sweeps on one GPU
+    parity = None
+    if world > 1 and not args.no_parity:
+        from poismf_b200.sharding import ShardedSweep
+        n_chk = 2
+        parity = {"sweeps": n_chk}
+        for tag, fl in (("", args.flags | FLAG_NO_LOCKSTEP), ("lockstep_", args.flags)):
+            pchk = make_params(cfg["method"], numiter=n_chk, flags=fl, **cfg["hp"])
+            be.reset(A0, B0)
+            ShardedSweep(be, dimA, dimB, np.float32).run(pchk)
+            As, Bs = be.factors()
+            digest = hashlib.sha256(As.tobytes() + Bs.tobytes()).hexdigest()
+            alld = [None] * world
+            dist.all_gather_object(alld, digest)
+            same = len(set(alld)) == 1
+            rel = llk_rel = None
+            if rank == 0:
+                one = DeviceFit(dimA, dimB, k, np.float32, device=local_rank)
+                one.set_csr_csc(csr, csc); one.set_factors(A0, B0)
+                one.sweeps(pchk); one.sync()
+                A1, B1 = one.get_factors()
+                one.close()
+                rel = max(float(np.abs(As - A1).max() / max(np.abs(A1).max(), 1e-30)),
+                          float(np.abs(Bs - B1).max() / max(np.abs(B1).max(), 1e-30)))
+                try:
+                    from oracle.oracle import Restatement
+                    orc = Restatement(np.float32)
+                    l1, ls = orc.llk(A1, B1, csr), orc.llk(As, Bs, csr)
+                    llk_rel = abs(ls - l1) / abs(l1)
+                except Exception:
+                    pass
+            parity[tag + "ranks_identical"] = bool(same)
+            parity[tag + "vs_single_gpu_max_rel"] = rel
+            parity[tag + "llk_rel"] = llk_rel
+        parity["note"] = ("ranks_identical / vs_single_gpu_max_rel: per-row teams only (PMF_FLAG_NO_LOCKSTEP), whose bits do not "
+                          "depend on the partition; lockstep_*: default flags, the heaviest rows' non-zeros are summed in an order "
+                          "that depends on which heavy rows a rank holds (cg in float is chaotic in the rounding: compare llk)")
+
+    # e2e: drop-in run_poismf with host buffers (rank 0 alone at N=1; the sharded public API otherwise)
+    e2e = e2e_pageable = None
     if not args.no_e2e and world == 1:
-        hA, hB = A0.copy(), B0.copy()
-        pin = []
-        for arr in (csr[0], csr[1], csr[2], csc[0], csc[1], csc[2], hA, hB):
-            t = torch.from_numpy(arr)
-            try:
-                torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
-                pin.append(t)
-            except Exception:
-                pass
         h2d = sum(a.nbytes for a in (csr[0], csr[1], csr[2], csc[0], csc[1], csc[2], A0, B0))
         d2h = A0.nbytes + B0.nbytes
         e_steps = max(3, min(args.steps, 5))
+        hA, hB = A0.copy(), B0.copy()
+
         def one():
             hA[...] = A0; hB[...] = B0
             t0 = time.perf_counter()
@@ -329,12 +471,23 @@ def main():
                                step_size=cfg["hp"].get("step_size", 1e-7), niter=1, maxupd=cfg["hp"]["maxupd"],
                                early_stop=False, reuse_prev=False, flags=args.flags)
             return time.perf_counter() - t0
-        one()
-        ts = [one() for _ in range(e_steps)]
-        e_ms = 1e3 * float(np.mean(ts))
-        e2e = {"value": nnz / (e_ms / 1e3), "unit": "nnz/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms, "steps": e_steps,
-               "call": "run_poismf(numiter=1) via C ABI, host buffers (cudaHostRegister'ed), upload+plan+sweep+download"}
+
+        def timed(call):
+            one()
+            e_ms = 1e3 * float(np.mean([one() for _ in range(e_steps)]))
+            return {"value": nnz / (e_ms / 1e3), "unit": "nnz/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms, "steps": e_steps, "call": call}
+        e2e_pageable = timed("run_poismf(numiter=1) via C ABI, ordinary pageable numpy buffers (staged through page-locked "
+                             "blocks by host threads), upload+plan+sweep+download")
+        pin = []
+        for arr in (csr[0], csr[1], csr[2], csc[0], csc[1], csc[2], hA, hB):
+            t = torch.from_numpy(arr)
+            try:
+                torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+                pin.append(t)
+            except Exception:
+                pass
+        e2e = timed("run_poismf(numiter=1) via C ABI, host buffers (cudaHostRegister'ed), upload+plan+sweep+download")
         for t in pin:
             try:
                 torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
@@ -342,26 +495,23 @@ def main():
                 pass
 
     if not args.no_e2e and world > 1:
-        # sharded public API end to end: every rank uploads ITS row/column shard and the replicated
-        # factors from host memory, runs one sharded sweep (NCCL exchange inside), reads A,B back
-        from poismf_b200.sharding import GpuBackend, ShardedSweep
-        del be
-        torch.cuda.synchronize()
+        # sharded public API end to end on the PERSISTENT backend (handles, peer mappings and epoch slots are
+        # set up once per process group): every rank uploads ITS row/column shard and the replicated factors
+        # from host memory, runs one sharded sweep, reads A,B back
+        from poismf_b200.sharding import ShardedSweep
         ts = []
         h2d = d2h = 0
-        for it in range(3):
+        for it in range(4):
             dist.barrier()
             t0 = time.perf_counter()
-            be2 = GpuBackend(csr, csc, A0, B0, rank, world, local_rank, exchange=args.exchange)
-            ShardedSweep(be2, dimA, dimB, np.float32).run(params)
-            Aout, Bout = be2.factors()
-            torch.cuda.synchronize()
+            be.load(csr, csc, A0, B0)
+            ShardedSweep(be, dimA, dimB, np.float32).run(params)
+            be.factors()
             dt = time.perf_counter() - t0
-            a0, a1 = be2.rangesA[rank]; b0, b1 = be2.rangesB[rank]
+            a0, a1 = be.rangesA[rank]; b0, b1 = be.rangesB[rank]
             h2d = (A0.nbytes + B0.nbytes + int(csr[1][a1] - csr[1][a0]) * 12 + int(csc[1][b1] - csc[1][b0]) * 12
                    + (a1 - a0 + b1 - b0) * 8)
             d2h = A0.nbytes + B0.nbytes
-            del be2
             if it > 0:
                 ts.append(dt)
         t = torch.tensor([float(np.mean(ts))], device="cuda", dtype=torch.float64)
@@ -369,21 +519,26 @@ def main():
         e_ms = 1e3 * float(t.item())
         e2e = {"value": nnz / (e_ms / 1e3), "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e_ms, "steps": len(ts),
-               "call": "poismf_b200.sharding.GpuBackend + ShardedSweep.run(numiter=1) + factors(): per-rank shard upload, sweep with NCCL exchange, download (max over ranks)"}
+               "call": "GpuBackend.load + ShardedSweep.run(numiter=1) + factors() on a persistent backend: per-rank shard "
+                       "upload, plan, sweep with the fused exchange, download (max over ranks)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            _, _, cpu = run_reference(cfg, 3, 1)
+            _, cpu = run_reference(cfg, problem, 3)
         except Exception as e:  # the oracle is optional infrastructure for this leg
             cpu = {"value": None, "unit": "nnz/s per sweep", "cores": 0, "kind": "unavailable", "sample": str(e)}
 
     if rank == 0:
-        line = {"metric": "nnz processed/sec per alternating sweep", "value": value, "unit": "nnz/s",
+        line = {"metric": metric, "value": value, "unit": "nnz/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_line, "nnz": nnz, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
+        if e2e_pageable is not None:
+            line["e2e_pageable"] = e2e_pageable
+        if parity is not None:
+            line["parity"] = parity
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -95,11 +95,16 @@ int pmf_b200_sync(pmf_b200_handle* h);
  * Sharded fits keep a replica of A and B on every GPU.  Instead of an NCCL collective after
  * each half-sweep, the row kernels store every freshly solved row straight into the peers'
  * replicas (plain stores to peer-mapped pointers; one process per GPU, so the mapping goes
- * through CUDA IPC).  The caller only needs a stream sync + a process barrier between
- * half-sweeps.  Usage: every rank exports its two factor buffers (64-byte handles), the
- * handles are all-gathered by the caller (e.g. torch.distributed), every rank imports them. */
+ * through CUDA IPC).  Usage: every rank exports its two factor buffers (64-byte handles), the
+ * handles are all-gathered by the caller (e.g. torch.distributed), every rank imports them.
+ * Completion is signalled ON THE DEVICE when the ranks also exchange `which = 2`, their epoch
+ * slots: after its half-sweep a rank writes the half-sweep's number into its slot on every
+ * rank, and the next half-sweep's kernels are preceded by a one-warp kernel that waits until
+ * all slots have reached it.  The host then enqueues whole fits without waiting between
+ * half-sweeps (without the slots the caller needs a stream sync + a process barrier there).
+ * pmf_b200_sync returns 1 if a peer failed to arrive within ~30 s. */
 #define PMF_B200_IPC_HANDLE_BYTES 64
-int pmf_b200_ipc_export(pmf_b200_handle* h, int which /*0=A,1=B*/, void* handle_out);
+int pmf_b200_ipc_export(pmf_b200_handle* h, int which /*0=A,1=B,2=epoch slots*/, void* handle_out);
 /* handles: n_ranks x 64 bytes in rank order (own entry ignored).  n_ranks <= 8. */
 int pmf_b200_ipc_import(pmf_b200_handle* h, int which, const void* handles, int n_ranks, int self_rank);
 

@@ -190,6 +190,7 @@ struct pmf_b200_handle {
     virtual size_t side_nnz(int side) const = 0;
     virtual int ipc_export(int which, void* out) = 0;
     virtual int ipc_import(int which, const void* handles, int n_ranks, int self_rank) = 0;
+    virtual int exchange_status() = 0;
     virtual int get_profile(pmf_b200_bin_profile* out, int max_entries) = 0;
     virtual void clear_profile() = 0;
     bool profiling = false;
@@ -212,6 +213,13 @@ template <class real> struct HandleT : pmf_b200_handle {
     // small or latency-bound bins overlap (fork from / join to the handle's stream with events)
     real* peer[2][7] = {};      // peers' replicas of A (0) and B (1), opened through CUDA IPC
     int npeers[2] = {0, 0};
+    // device-side completion of the exchange: own epoch slots (raw cudaMalloc: exported), the ranks' slot arrays
+    unsigned long long* sig = nullptr;
+    int* sig_status = nullptr;
+    PeerSignals sigs = {};
+    void* sig_opened[7] = {};
+    int n_sig_opened = 0;
+    unsigned long long epoch = 0;
     bool exported[2] = {false, false};   // A / B handed to other processes: never recycled through the block cache
     static constexpr int NAUX = 6;
     cudaStream_t aux[NAUX] = {};
@@ -229,6 +237,9 @@ template <class real> struct HandleT : pmf_b200_handle {
         sides[0].free_all(); sides[1].free_all();
         for (int w = 0; w < 2; w++)
             for (int q = 0; q < npeers[w]; q++) cudaIpcCloseMemHandle(peer[w][q]);
+        for (int q = 0; q < n_sig_opened; q++) cudaIpcCloseMemHandle(sig_opened[q]);
+        if (sig) cudaFree(sig);
+        if (sig_status) cudaFree(sig_status);
         if (ownA && A) { if (exported[0]) DevPool::get().discard(A); else dfree(A); }
         if (ownB && B) { if (exported[1]) DevPool::get().discard(B); else dfree(B); }
         if (csum) dfree(csum);
@@ -855,6 +866,11 @@ template <class real> struct HandleT : pmf_b200_handle {
         hc.early_stop = (p.method == PMF_TNCG && p.early_stop) ? 1 : 0;
         hc.method = p.method;
 
+        // sharded fit with device-side completion: every rank's previous half-sweep must have landed
+        if (sigs.n_ranks > 1 && epoch > 0) {
+            wait_epoch_kernel<<<1, 32, 0, stream>>>(sig, sigs.n_ranks, epoch, sig_status);
+            LAUNCHED();
+        }
         ColsumFinal<real> fin;
         fin.l1 = l1; fin.scale1 = -step; fin.scale2 = -step; fin.nscale = 0;
         if (p.method == PMF_PG && w == (real)1) fin.nscale = updA ? 2 : 1;   // Q1: A side scaled twice
@@ -957,16 +973,41 @@ template <class real> struct HandleT : pmf_b200_handle {
                     CK(cudaEventRecord(ev_join[si], aux[si]));
                     CK(cudaStreamWaitEvent(stream, ev_join[si], 0));
                 }
+        if (sigs.n_ranks > 1) {
+            epoch++;
+            signal_epoch_kernel<<<1, 1, 0, stream>>>(sigs, epoch);
+            LAUNCHED();
+        }
         if (hc.early_stop && n_unchanged) {
             CK(cudaMemcpyAsync(n_unchanged, d_unchanged, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
         }
         return 0;
     }
+    // 1 if a peer failed to arrive at an exchange point (the fit's results are then invalid)
+    int exchange_status() override
+    {
+        if (!sig_status) return 0;
+        int v = 0;
+        cudaMemcpy(&v, sig_status, sizeof v, cudaMemcpyDeviceToHost);
+        return v;
+    }
 
     int ipc_export(int which, void* out) override
     {
         CK(cudaSetDevice(device));
+        if (which == 2) {          // the epoch slots of the device-side exchange completion
+            if (!sig) {
+                CK(cudaMalloc(&sig, 8 * sizeof(unsigned long long)));
+                CK(cudaMemset(sig, 0, 8 * sizeof(unsigned long long)));
+                CK(cudaMalloc(&sig_status, sizeof(int)));
+                CK(cudaMemset(sig_status, 0, sizeof(int)));
+            }
+            cudaIpcMemHandle_t hd;
+            CK(cudaIpcGetMemHandle(&hd, (void*)sig));
+            memcpy(out, &hd, sizeof hd);
+            return 0;
+        }
         if ((which == 0 && !ownA) || (which == 1 && !ownB))
             return fail("ipc_export: factors are bound to caller memory; export needs handle-owned buffers");
         cudaIpcMemHandle_t hd;
@@ -980,6 +1021,22 @@ template <class real> struct HandleT : pmf_b200_handle {
     {
         CK(cudaSetDevice(device));
         if (n_ranks < 1 || n_ranks > 8) return fail("ipc_import: 1..8 ranks");
+        if (which == 2) {
+            if (!sig) return fail("ipc_import: export the epoch slots first");
+            for (int q = 0; q < n_sig_opened; q++) cudaIpcCloseMemHandle(sig_opened[q]);
+            n_sig_opened = 0;
+            sigs.n_ranks = n_ranks; sigs.self = self_rank;
+            for (int r = 0; r < n_ranks; r++) {
+                if (r == self_rank) { sigs.slot[r] = sig; continue; }
+                cudaIpcMemHandle_t hd;
+                memcpy(&hd, (const char*)handles + (size_t)r * sizeof hd, sizeof hd);
+                void* ptr = nullptr;
+                CK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+                sig_opened[n_sig_opened++] = ptr;
+                sigs.slot[r] = (unsigned long long*)ptr;
+            }
+            return 0;
+        }
         for (int q = 0; q < npeers[which]; q++) cudaIpcCloseMemHandle(peer[which][q]);
         npeers[which] = 0;
         for (int r = 0; r < n_ranks; r++) {
@@ -1355,6 +1412,7 @@ extern "C" int pmf_b200_sync(pmf_b200_handle* h)
 {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->exchange_status()) return fail("sharded fit: a peer did not arrive at an exchange point");
     return 0;
 }
 

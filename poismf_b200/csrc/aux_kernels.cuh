@@ -117,6 +117,38 @@ __global__ void zero_rows_kernel(real* __restrict__ M, const int* __restrict__ r
     }
 }
 
+// ---- device-side completion of the fused exchange (sharded fits) ----------------------------------------
+// Every rank owns 8 epoch slots in peer-mapped memory.  After the kernels of half-sweep e (whose row
+// epilogues stored the solved rows into every replica) a one-thread kernel writes e into slot `self` of
+// every rank; before the kernels of half-sweep e+1 a one-warp kernel spins until all of ITS OWN slots
+// have reached e.  The host never waits between half-sweeps.  (Waiting for ALL ranks also covers the
+// write-after-read hazard: nobody overwrites rows of a matrix a slower rank is still reading.)
+struct PeerSignals {
+    unsigned long long* slot[8];     // slot[r]: rank r's epoch array (own entry included)
+    int n_ranks, self;
+};
+__global__ void signal_epoch_kernel(PeerSignals S, unsigned long long epoch)
+{
+    __threadfence_system();
+    for (int r = 0; r < S.n_ranks; r++) *reinterpret_cast<volatile unsigned long long*>(S.slot[r] + S.self) = epoch;
+    __threadfence_system();
+}
+// `status` (device int, host-mapped copy checked by the caller) is set to 1 if a peer does not arrive
+// within ~30 s: the fit then fails instead of hanging the GPU
+__global__ void wait_epoch_kernel(const unsigned long long* own, int n_ranks, unsigned long long epoch, int* status)
+{
+    const int r = threadIdx.x;
+    if (r < n_ranks) {
+        const volatile unsigned long long* s = own + r;
+        const long long t0 = clock64();
+        while (*s < epoch) {
+            __nanosleep(200);
+            if (clock64() - t0 > 60000000000LL) { *status = 1; break; }
+        }
+    }
+    __threadfence_system();
+}
+
 // out[i] = <A[ixA[i]], B[ixB[i]]>, summed left to right without contraction: the
 // same bits as the reference's sequential dot.  One thread per pair; each thread
 // streams its two factor rows with 16-byte loads (the path is a pure gather,

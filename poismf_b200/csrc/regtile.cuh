@@ -34,52 +34,51 @@ namespace pmf {
 constexpr unsigned RT_FULL = 0xffffffffu;
 
 template <int NW> struct RtShared {
-    float part[2][NW][32][4];     // per-warp partial k-vectors (OWN <= 4 floats per lane), double-buffered
-    float red[2][4][NW];          // per-warp partial sums over non-zeros (<= 4 at a time), double-buffered
+    float fold[NW][4][8][4][4];   // per warp: [chunk slot j][tg][ig][4]: the 8 tg-lanes' partial k-vectors of the gaxpy pass
+    float part[2][NW][64];        // per-warp folded partial k-vectors, double-buffered (NW > 1)
+    float red[2][8][NW];          // per-warp partial sums over non-zeros (<= 8 at a time), double-buffered
+    float dsh[64];                // the search direction, written by the k-phase warp, read in chunk layout by all
+    float ksc[8];                 // k-scalars of the iteration: <g,d>, |d|^2, |g|^2, <csum + 2 l2 x, d>, max step
     int next_row;
 };
 
-// one step of a reduce-scatter over the lane pairs (lane, lane ^ mask): the lane whose bit is set
-// keeps the upper half of v[0..N), its partner the lower half
-template <int N> PMF_DEVINL void rt_rs_step(float* v, int mask, bool upper)
+PMF_DEVINL float rt_redux_min(float v)
 {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// sums of N = 2, 4 or 8 values over the 32 lanes of a warp with a transposing butterfly: after the call
+// v[0] of the lanes whose TOP log2(N) lane bits spell j holds the sum of value j  (N-1 + 5-log2(N) shuffles
+// instead of 5 N)
+template <int N> PMF_DEVINL void rt_packed_sum(float (&v)[N], int lane)
+{
+    static_assert(N == 2 || N == 4 || N == 8, "2, 4 or 8 values");
+    if (N >= 8) {
+        const bool up = (lane & 16) != 0;
 #pragma unroll
-    for (int i = 0; i < N / 2; i++) {
-        const float send = upper ? v[i] : v[i + N / 2];
-        const float keep = upper ? v[i + N / 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(RT_FULL, send, mask);
+        for (int i = 0; i < 4; i++) {
+            const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(RT_FULL, send, 16);
+        }
     }
-}
-
-template <int N> PMF_DEVINL void rt_warp_sum(float (&v)[N])
-{
+    if (N >= 4) {
+        constexpr int M = N >= 8 ? 8 : 16;
+        const bool up = (lane & M) != 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+        for (int i = 0; i < 2; i++) {
+            const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(RT_FULL, send, M);
+        }
+    }
+    {
+        constexpr int M = N >= 8 ? 4 : (N >= 4 ? 8 : 16);
+        const bool up = (lane & M) != 0;
+        const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(RT_FULL, send, M);
 #pragma unroll
-        for (int j = 0; j < N; j++) v[j] += __shfl_xor_sync(RT_FULL, v[j], o);
-}
-
-// sums over the row's non-zeros: warp butterfly, then (NW > 1) the per-warp partials through shared
-// memory, folded by every warp in the same (butterfly) order
-template <int NW, int N>
-PMF_DEVINL void rt_team_sum(float (&v)[N], RtShared<NW>& sh, int& buf, int warp, int lane)
-{
-    static_assert(N <= 4, "at most 4 sums per reduction");
-    rt_warp_sum(v);
-    if (NW > 1) {
-        if (lane == 0)
-#pragma unroll
-            for (int j = 0; j < N; j++) sh.red[buf][j][warp] = v[j];
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < N; j++) v[j] = lane < NW ? sh.red[buf][j][lane] : 0.f;
-#pragma unroll
-        for (int o = NW >> 1; o > 0; o >>= 1)
-#pragma unroll
-            for (int j = 0; j < N; j++) v[j] += __shfl_xor_sync(RT_FULL, v[j], o);
-#pragma unroll
-        for (int j = 0; j < N; j++) v[j] = __shfl_sync(RT_FULL, v[j], 0);
-        buf ^= 1;
+        for (int o = M >> 1; o > 0; o >>= 1) v[0] += __shfl_xor_sync(RT_FULL, v[0], o);
     }
 }
 
@@ -121,53 +120,46 @@ PMF_DEVINL float rt_dots(const float4 (&T)[TPL][NC], const float4 (&v)[NC], int 
     }
 }
 
-// out[i] = (sum over the team's non-zeros of c_t F_t)[component owned by this lane, i]
+// out[i] = (sum over THIS WARP's non-zeros of c_t F_t)[component owned by this lane, i].  The 8 tg-lanes'
+// partial vectors are folded through the warp's 2 KB of shared memory (4 STS.128 + 8 LDS.64 per lane, fixed
+// order) rather than by shuffles: a third of the instructions of a transposing butterfly.
 template <int NC, int TPL, int NW>
-PMF_DEVINL void rt_gaxpy(const float4 (&T)[TPL][NC], float c, float (&out)[NC / 2], RtShared<NW>& sh, int& buf,
-                         int warp, int lane)
+PMF_DEVINL void rt_gaxpy(const float4 (&T)[TPL][NC], float c, float (&out)[NC / 2], RtShared<NW>& sh, int warp, int lane)
 {
     constexpr int OWN = NC / 2;
+    const int ig = lane & 3, tg = lane >> 2;
     float cs[TPL];
 #pragma unroll
     for (int s = 0; s < TPL; s++) cs[s] = __shfl_sync(RT_FULL, c, (lane & ~3) | s);
-    float v[4 * NC];
+    __syncwarp();                                   // the previous fold's readers are done
 #pragma unroll
     for (int j = 0; j < NC; j++) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int s = 0; s < TPL; s++) vfma(a, cs[s], T[s][j]);
-        v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+        *reinterpret_cast<float4*>(&sh.fold[warp][j][tg][ig][0]) = a;      // 32 lanes: 512 contiguous bytes
     }
-    rt_rs_step<4 * NC>(v, 16, (lane & 16) != 0);
-    rt_rs_step<2 * NC>(v, 8, (lane & 8) != 0);
-    rt_rs_step<NC>(v, 4, (lane & 4) != 0);
-    if (NW > 1) {
+    __syncwarp();
 #pragma unroll
-        for (int i = 0; i < OWN; i++) sh.part[buf][warp][lane][i] = v[i];
-        __syncthreads();
+    for (int i = 0; i < OWN; i++) out[i] = 0.f;
+    // owned components: flat elements tg*OWN + i of this lane's 4 NC (chunk slot (tg*OWN + i) / 4)
 #pragma unroll
-        for (int i = 0; i < OWN; i++) {
-            float s = 0.f;
+    for (int t = 0; t < 8; t++) {
+        if (OWN == 2) {
+            const float2 v = *reinterpret_cast<const float2*>(&sh.fold[warp][tg >> 1][t][ig][(tg & 1) * 2]);
+            out[0] += v.x; out[1] += v.y;
+        } else {
 #pragma unroll
-            for (int w = 0; w < NW; w++) s += sh.part[buf][w][lane][i];
-            out[i] = s;
+            for (int i = 0; i < OWN; i++) out[i] += sh.fold[warp][(tg * OWN + i) >> 2][t][ig][(tg * OWN + i) & 3];
         }
-        buf ^= 1;
-    } else {
-#pragma unroll
-        for (int i = 0; i < OWN; i++) out[i] = v[i];
     }
 }
 
-// the lane's chunk layout of a k-vector from its owned layout
-template <int NC> PMF_DEVINL void rt_allgather(const float (&own)[NC / 2], float4 (&out)[NC], int ig)
+// the lane's chunk layout of the k-vector in sh.dsh (component order)
+template <int NC, int NW> PMF_DEVINL void rt_read_dir(const RtShared<NW>& sh, float4 (&out)[NC], int ig)
 {
-    constexpr int OWN = NC / 2;
-    float v[4 * NC];
 #pragma unroll
-    for (int e = 0; e < 4 * NC; e++) v[e] = __shfl_sync(RT_FULL, own[e % OWN], ((e / OWN) << 2) | ig);
-#pragma unroll
-    for (int j = 0; j < NC; j++) out[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < NC; j++) out[j] = *reinterpret_cast<const float4*>(&sh.dsh[4 * (ig + 4 * j)]);
 }
 
 // resident CTAs per SM the kernels are compiled for: 16 warps per SM when a lane holds 4 tile rows
@@ -181,7 +173,7 @@ template <int NC, int TPL, int NW> struct RtCfg {
 template <int NC, int TPL, int NW, int METHOD>
 __global__ void __launch_bounds__(32 * NW, RtCfg<NC, TPL, NW>::min_ctas) rows_regtile_kernel(const SideParams<float> P)
 {
-    static_assert(NC % 2 == 0 && NC <= 8 && TPL >= 1 && TPL <= 4, "unsupported register tile");
+    static_assert(NC % 2 == 0 && NC <= 4 && TPL >= 1 && TPL <= 4, "unsupported register tile");
     constexpr int OWN = NC / 2;
     constexpr int PS = TPL <= 1 ? 1 : (TPL <= 2 ? 2 : 4);
     __shared__ RtShared<NW> sh;
@@ -249,132 +241,189 @@ __global__ void __launch_bounds__(32 * NW, RtCfg<NC, TPL, NW>::min_ctas) rows_re
             cs[i] = gi[i] < k ? P.csum[gi[i]] : 0.f;
         }
 
+        // k-vector phases are executed by warp 0 only (NW > 1: the other warps wait at the barrier instead
+        // of repeating them); its lanes own the row's components
+        const bool kwarp = warp == 0;
+        auto team_sync = [&]() { if (NW > 1) __syncthreads(); else __syncwarp(); };
+        // fold of the per-warp partial k-vectors (fixed order), by the k-phase warp
+        auto fold_parts = [&](float (&v)[OWN]) {
+            if (NW > 1) {
+#pragma unroll
+                for (int i = 0; i < OWN; i++) sh.part[buf][warp][lane * OWN + i] = v[i];
+                __syncthreads();
+                if (kwarp) {
+#pragma unroll
+                    for (int i = 0; i < OWN; i++) v[i] = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NW; w++)
+#pragma unroll
+                        for (int i = 0; i < OWN; i++) v[i] += sh.part[buf][w][lane * OWN + i];
+                }
+                buf ^= 1;
+            }
+        };
+        // the k-phase warp publishes a k-vector (owned layout -> component order) for everybody's chunk layout
+        auto publish = [&](const float (&v)[OWN]) {
+            if (kwarp) {
+#pragma unroll
+                for (int i = 0; i < OWN; i++) sh.dsh[gi[i]] = v[i];       // gi[0..OWN) are consecutive components
+            }
+        };
+
         if (METHOD == M_PG) {
             // ---- pg (src/poismf.c:172-185); cs = pre-scaled column sums -----------------------
             for (int u = 0; u < hc.maxupd; u++) {
                 const float p = rt_dots<NC, TPL>(T, vd, ig);
                 const float c = act ? xval / p : 0.f;
                 float g[OWN];
-                rt_gaxpy<NC, TPL, NW>(T, c, g, sh, buf, warp, lane);
+                rt_gaxpy<NC, TPL, NW>(T, c, g, sh, warp, lane);
+                fold_parts(g);
+                if (kwarp) {
 #pragma unroll
-                for (int i = 0; i < OWN; i++) {
-                    float v = fmaf(hc.step_w, g[i], xo[i]);
-                    v += cs[i];
-                    v *= hc.cdiv;
-                    xo[i] = (v > 0.f) ? v : 0.f;
+                    for (int i = 0; i < OWN; i++) {
+                        float v = fmaf(hc.step_w, g[i], xo[i]);
+                        v += cs[i];
+                        v *= hc.cdiv;
+                        xo[i] = (v > 0.f) ? v : 0.f;
+                    }
                 }
-                if (u + 1 < hc.maxupd) rt_allgather<NC>(xo, vd, ig);
+                if (u + 1 < hc.maxupd) {
+                    team_sync();            // the previous readers of dsh are done
+                    publish(xo);
+                    team_sync();
+                    rt_read_dir<NC, NW>(sh, vd, ig);
+                }
             }
         } else {
             // ---- cg, cached line search (solve_cg_cached) ------------------------------------
-            const float tol = 1e-2f, decr = 0.25f, c_ls = 0.01f;
+            const float tol = 1e-2f, c_ls = 0.01f;
             const int max_ls = 20, maxnfeval = 150;
             const int maxiter = hc.maxupd <= 0 ? INT32_MAX : hc.maxupd;
+            const float xl = xval * 0.693147180559945f;            // x_t ln 2: x log p = xl * log2 p
             float p = rt_dots<NC, TPL>(T, vd, ig);                  // p_t = <x, F_t>
-            float cft = act ? -xval / p : 0.f;                      // gradient coefficients
+            float cft = act ? __fdividef(-xval, p) : 0.f;           // gradient coefficients
             float fcur, regx;
             {
-                float r[3] = {act ? xlogp(xval, p) : 0.f, 0.f, 0.f};
+                float r[4] = {act ? xl * __log2f(p) : 0.f, 0.f, 0.f, 0.f};
+                if (kwarp) {
 #pragma unroll
-                for (int i = 0; i < OWN; i++) { r[1] = fmaf(cs[i], xo[i], r[1]); r[2] = fmaf(xo[i], xo[i], r[2]); }
-                float ls[1] = {r[0]};
-                rt_team_sum<NW, 1>(ls, sh, buf, warp, lane);
-                float kk[2] = {r[1], r[2]};
-                rt_warp_sum(kk);
-                regx = fmaf(hc.l2, kk[1], kk[0]);
-                fcur = regx - ls[0] * hc.w;                         // nonnegcg.c:191
+                    for (int i = 0; i < OWN; i++) { r[1] = fmaf(cs[i], xo[i], r[1]); r[2] = fmaf(xo[i], xo[i], r[2]); }
+                }
+                rt_packed_sum<4>(r, lane);                          // lanes 0 / 8 / 16: the three sums of this warp
+                if ((lane & 7) == 0 && lane < 24) sh.red[buf][lane >> 3][warp] = r[0];
+                team_sync();
+                float ls = 0.f;
+#pragma unroll
+                for (int w = 0; w < NW; w++) ls += sh.red[buf][0][w];
+                regx = fmaf(hc.l2, sh.red[buf][2][0], sh.red[buf][1][0]);
+                fcur = regx - ls * hc.w;                            // nonnegcg.c:191
+                buf ^= 1;
             }
             float go[OWN], gpo[OWN], dpo[OWN], dn[OWN];
 #pragma unroll
-            for (int i = 0; i < OWN; i++) { gpo[i] = 0.f; dpo[i] = 0.f; }
+            for (int i = 0; i < OWN; i++) { gpo[i] = 0.f; dpo[i] = 0.f; go[i] = 0.f; dn[i] = 0.f; }
             float gprev_sq = 0.f, fnew = 0.f;
             int nfe = 1;
             bool stop = is_bad(fcur);
             for (int it = 0; it < maxiter && !stop; it++) {
                 // gradient at x (:231): one tile pass, folded onto csum + 2 l2 x
-                rt_gaxpy<NC, TPL, NW>(T, cft, go, sh, buf, warp, lane);
+                rt_gaxpy<NC, TPL, NW>(T, cft, go, sh, warp, lane);
+                fold_parts(go);
+                if (kwarp) {
 #pragma unroll
-                for (int i = 0; i < OWN; i++) go[i] = fmaf(hc.two_l2, xo[i], cs[i]) + go[i];
-                // direction (:236-261) and every k-scalar of this iteration
-                float theta = 0.f, beta = 0.f;
-                if (it > 0) {
-                    float tb[2] = {0.f, 0.f};
+                    for (int i = 0; i < OWN; i++) go[i] = fmaf(hc.two_l2, xo[i], cs[i]) + go[i];
+                    // direction (:236-261) and every k-scalar of this iteration
+                    float theta = 0.f, beta = 0.f;
+                    if (it > 0) {
+                        float tb[2] = {0.f, 0.f};
 #pragma unroll
-                    for (int i = 0; i < OWN; i++)
-                        if (!(xo[i] <= 0.f)) {
-                            tb[0] = fmaf(go[i], dpo[i], tb[0]);
-                            tb[1] = fmaf(go[i], go[i] - gpo[i], tb[1]);
-                        }
-                    rt_warp_sum(tb);
-                    theta = tb[0] / gprev_sq;
-                    beta = tb[1] / gprev_sq;
+                        for (int i = 0; i < OWN; i++)
+                            if (!(xo[i] <= 0.f)) {
+                                tb[0] = fmaf(go[i], dpo[i], tb[0]);
+                                tb[1] = fmaf(go[i], go[i] - gpo[i], tb[1]);
+                            }
+                        rt_packed_sum<2>(tb, lane);                 // lanes < 16: theta's sum, lanes >= 16: beta's
+                        const float t0 = __shfl_sync(RT_FULL, tb[0], 0), t1 = __shfl_sync(RT_FULL, tb[0], 16);
+                        const float inv = 1.f / gprev_sq;
+                        theta = t0 * inv;
+                        beta = t1 * inv;
+                    }
+                    float sc[4] = {0.f, 0.f, 0.f, 0.f};    // <g,d>, |d|^2, |g|^2, <csum + 2 l2 x, d>
+                    float m = 1.f;
+#pragma unroll
+                    for (int i = 0; i < OWN; i++) {
+                        const float xi = xo[i], g_i = go[i];
+                        float di = (xi <= 0.f && g_i >= 0.f) ? 0.f : -g_i;
+                        if (it > 0 && !(xi <= 0.f)) di += beta * dpo[i] - theta * (g_i - gpo[i]);
+                        dn[i] = di;
+                        sc[0] = fmaf(g_i, di, sc[0]); sc[1] = fmaf(di, di, sc[1]); sc[2] = fmaf(g_i, g_i, sc[2]);
+                        sc[3] = fmaf(fmaf(hc.two_l2, xi, cs[i]), di, sc[3]);
+                        if (di < 0.f) { const float r = -xi / di; m = (r < m) ? r : m; }        // limit_step (:272-279)
+                    }
+                    rt_packed_sum<4>(sc, lane);                     // lanes 0 / 8 / 16 / 24 hold the four sums
+                    m = rt_redux_min(m);
+                    if ((lane & 7) == 0) sh.ksc[lane >> 3] = sc[0];
+                    if (lane == 0) sh.ksc[4] = m;
                 }
-                float sc[4] = {0.f, 0.f, 0.f, 0.f};    // <g,d>, |d|^2, |g|^2, <csum + 2 l2 x, d>
-                float m = 1.f;
-#pragma unroll
-                for (int i = 0; i < OWN; i++) {
-                    const float xi = xo[i], g_i = go[i];
-                    float di = (xi <= 0.f && g_i >= 0.f) ? 0.f : -g_i;
-                    if (it > 0 && !(xi <= 0.f)) di += beta * dpo[i] - theta * (g_i - gpo[i]);
-                    dn[i] = di;
-                    sc[0] = fmaf(g_i, di, sc[0]); sc[1] = fmaf(di, di, sc[1]); sc[2] = fmaf(g_i, g_i, sc[2]);
-                    sc[3] = fmaf(fmaf(hc.two_l2, xi, cs[i]), di, sc[3]);
-                    if (di < 0.f) { const float r = -xi / di; m = (r < m) ? r : m; }        // limit_step (:272-279)
-                }
-                rt_warp_sum(sc);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { const float w2 = __shfl_xor_sync(RT_FULL, m, o); m = w2 < m ? w2 : m; }
-                const float gd = sc[0], dsq = sc[1], gg = sc[2], lin = sc[3], smax = m;
+                team_sync();                 // (also: the previous readers of dsh are past their tile pass)
+                const float gd = sh.ksc[0], dsq = sh.ksc[1], gg = sh.ksc[2], lin = sh.ksc[3], smax = sh.ksc[4];
                 if (fabs((double)gd) <= (double)tol) break;                                  // :264-269
-
-                rt_allgather<NC>(dn, vd, ig);
+                publish(dn);
+                team_sync();
+                rt_read_dir<NC, NW>(sh, vd, ig);
                 const float q = rt_dots<NC, TPL>(T, vd, ig);                                 // q_t = <d, F_t>
 
-                // line search (:297-327): first trial alone, then four at a time
-                float step = smax;
+                // line search (:297-327): trial steps smax 4^-j, FOUR per reduction round; lane group j = lane / 8
+                // ends with trial j's sum; the first acceptable trial in sequence order wins
                 bool accepted = false;
+                float step = 0.f;
                 const float l2dd = hc.l2 * dsq;
                 auto freg = [&](float sj) { return fmaf(sj, fmaf(sj, l2dd, lin), regx); };
-                {
-                    float ls[1] = {act ? xlogp(xval, fmaf(step, q, p)) : 0.f};
-                    rt_team_sum<NW, 1>(ls, sh, buf, warp, lane);
-                    fnew = freg(step) - ls[0] * hc.w;
-                    if (!is_bad(fnew) && fnew <= fcur - c_ls * step * dsq) accepted = true;
-                    else { nfe++; if (nfe >= maxnfeval) stop = true; }
-                }
-                int lsn = 1;
-                while (!accepted && !stop && lsn < max_ls) {
-                    constexpr int NB = 4;
-                    const int nb = (max_ls - lsn) < NB ? (max_ls - lsn) : NB;
-                    float steps[NB], lsv[NB];
+                auto pow4 = [](int e) { return __int_as_float((127 - 2 * e) << 23); };       // 4^-e, exact
+                for (int base = 0; base < max_ls && !accepted && !stop; base += 4) {
+                    float lsv[4];
                     {
-                        float sj = step * decr;
+                        float sj = smax * pow4(base);
 #pragma unroll
-                        for (int j = 0; j < NB; j++) { steps[j] = sj; sj *= decr; }
+                        for (int j = 0; j < 4; j++) { lsv[j] = xl * __log2f(fmaf(sj, q, p)); sj *= 0.25f; }
                     }
+                    if (!act) { lsv[0] = 0.f; lsv[1] = 0.f; lsv[2] = 0.f; lsv[3] = 0.f; }
+                    rt_packed_sum<4>(lsv, lane);
+                    const int jmine = lane >> 3;
+                    float tot = lsv[0];
+                    if (NW > 1) {
+                        if ((lane & 7) == 0) sh.red[buf][jmine][warp] = tot;
+                        __syncthreads();
+                        tot = 0.f;
 #pragma unroll
-                    for (int j = 0; j < NB; j++) lsv[j] = act ? xlogp(xval, fmaf(steps[j], q, p)) : 0.f;
-                    rt_team_sum<NW, NB>(lsv, sh, buf, warp, lane);
-#pragma unroll
-                    for (int j = 0; j < NB; j++) {
-                        if (j < nb && !accepted && !stop) {
-                            fnew = freg(steps[j]) - lsv[j] * hc.w;
-                            if (!is_bad(fnew) && fnew <= fcur - c_ls * steps[j] * dsq) { accepted = true; step = steps[j]; }
-                            else { nfe++; if (nfe >= maxnfeval) stop = true; }
-                        }
+                        for (int w = 0; w < NW; w++) tot += sh.red[buf][jmine][w];
+                        buf ^= 1;
                     }
-                    if (!accepted) { step = steps[nb - 1]; lsn += nb; }
+                    const float sj = smax * pow4(base + jmine);
+                    const float fj = freg(sj) - tot * hc.w;
+                    const bool okj = !is_bad(fj) && fj <= fcur - c_ls * sj * dsq;
+                    const unsigned okmask = __ballot_sync(RT_FULL, okj);
+                    const int firstok = okmask ? (__ffs(okmask) - 1) >> 3 : 4;
+                    const int fails_allowed = maxnfeval - nfe;      // the fails_allowed-th failed trial stops the solver
+                    int last;
+                    if (firstok < 4 && firstok < fails_allowed) { accepted = true; nfe += firstok; last = firstok; }
+                    else if (fails_allowed <= 4 && fails_allowed <= firstok) { stop = true; nfe += fails_allowed; last = fails_allowed - 1; }
+                    else { nfe += 4; last = 3; }
+                    fnew = __shfl_sync(RT_FULL, fj, 8 * last);
+                    step = __shfl_sync(RT_FULL, sj, 8 * last);
                 }
                 if (stop && !accepted) break;                                                // :317-320
                 if (accepted) {
                     regx = freg(step);
+                    if (kwarp) {
 #pragma unroll
-                    for (int i = 0; i < OWN; i++) {
-                        const float v = fmaf(step, dn[i], xo[i]);
-                        xo[i] = (v >= hc.clip_thr) ? v : 0.f;
+                        for (int i = 0; i < OWN; i++) {
+                            const float v = fmaf(step, dn[i], xo[i]);
+                            xo[i] = (v >= hc.clip_thr) ? v : 0.f;
+                        }
                     }
                     p = fmaf(step, q, p);
-                    cft = act ? -xval / p : 0.f;
+                    cft = act ? __fdividef(-xval, p) : 0.f;
                 }
                 fcur = fnew;                                                                 // :328 (Q4)
                 gprev_sq = gg;                                                               // :332

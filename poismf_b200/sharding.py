@@ -75,7 +75,9 @@ class ShardedSweep:
         self.be = backend
         self.dimA, self.dimB = dimA, dimB
         self.dtype = np.dtype(dtype)
-        self.allreduce_int = world_allreduce_int or (lambda v: v)
+        # tncg's early stop compares the number of unchanged rows of the WHOLE matrix with its dimension
+        # (src/poismf.c:393-403): the local counts are summed over ranks
+        self.allreduce_int = world_allreduce_int or getattr(backend, "allreduce_int", None) or (lambda v: v)
 
     def run(self, params):
         from . import _lib
@@ -108,8 +110,11 @@ class GpuBackend:
 
     exchange="p2p"  (default): the handle owns the replicas of A and B; their CUDA IPC handles are
         all-gathered once, and from then on the row kernels store every solved row directly into
-        all peers' replicas over NVLink (fused compute + exchange, include/poismf_b200.h).  The
-        exchange step left between half-sweeps is a stream sync + a process barrier.
+        all peers' replicas over NVLink (fused compute + exchange, include/poismf_b200.h).
+        Completion is signalled on the device (epoch slots in peer memory, a one-warp wait kernel
+        ahead of the next half-sweep): nothing is left for the host between half-sweeps, whole fits
+        are enqueued asynchronously.  `exchange="p2p-host"` keeps the r1 behaviour (stream sync +
+        process barrier after every half-sweep).
     exchange="nccl": replicas are torch tensors bound into the handle; after each half-sweep the
         owners' rows are broadcast in place (one NCCL broadcast per owner).
     """
@@ -134,11 +139,21 @@ class GpuBackend:
             tdt = torch.float32 if A0.dtype == np.float32 else torch.float64
             self.A = torch.zeros((dimA, ldf), dtype=tdt, device=self.dev)
             self.B = torch.zeros((dimB, ldf), dtype=tdt, device=self.dev)
-            self.A[:, :k].copy_(torch.from_numpy(A0))
-            self.B[:, :k].copy_(torch.from_numpy(B0))
             self.fit.bind_factors(self.A.data_ptr(), self.B.data_ptr())
-        else:
-            self.fit.set_factors(A0, B0)
+        if self.mode in ("p2p", "p2p-host"):
+            for which in ((0, 1, 2) if self.mode == "p2p" else (0, 1)):
+                mine = self.fit.ipc_export(which)
+                allh = [None] * world
+                dist.all_gather_object(allh, mine, group=group)
+                self.fit.ipc_import(which, allh, rank)
+        self.load(csr, csc, A0, B0)
+
+    def load(self, csr, csc, A0, B0):
+        """(Re-)upload this rank's row / column shard and the replicated factors from host memory; the
+        handle, its peer mappings and the epoch slots persist (a second fit on the same backend)."""
+        from . import _lib
+        self.finish()
+        world, rank = self.world, self.rank
         self.rangesA = nnz_balanced_ranges(csr[1], world)
         self.rangesB = nnz_balanced_ranges(csc[1], world)
         a0, a1 = self.rangesA[rank]
@@ -148,18 +163,9 @@ class GpuBackend:
         self.local_nnz = int(lr[0].shape[0])
         self.fit.set_matrix(_lib.SIDE_CSR, *lr, row_begin=a0, n_rows=a1 - a0)
         self.fit.set_matrix(_lib.SIDE_CSC, *lc, row_begin=b0, n_rows=b1 - b0)
-        if self.mode == "p2p":
-            for which in (0, 1):
-                mine = self.fit.ipc_export(which)
-                allh = [None] * world
-                dist.all_gather_object(allh, mine, group=group)
-                self.fit.ipc_import(which, allh, rank)
-        torch.cuda.synchronize(self.dev)
-        if world > 1:
-            dist.barrier(group=group)
+        self._set_factors(A0, B0)
 
-    def reset(self, A0, B0):
-        """Restore the initial factors on this rank's replica (bench warm-up)."""
+    def _set_factors(self, A0, B0):
         if self.mode == "nccl":
             self.A[:, :self.k].copy_(self.torch.from_numpy(A0))
             self.B[:, :self.k].copy_(self.torch.from_numpy(B0))
@@ -169,14 +175,31 @@ class GpuBackend:
         if self.world > 1:
             self.dist.barrier(group=self.group)
 
+    def reset(self, A0, B0):
+        """Restore the initial factors on this rank's replica (bench warm-up)."""
+        self.finish()           # nobody may still be storing rows into this replica
+        self._set_factors(A0, B0)
+
     def half_sweep(self, side, params, step, cdiv):
         return self.fit.half_sweep(side, params, step, cdiv)
 
+    def allreduce_int(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([int(v)], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def finish(self):
+        """Wait for everything enqueued on this rank (and, through the epoch slots, on its peers)."""
+        self.fit.sync()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
     def exchange(self, side):
-        if self.mode == "local":
-            return
-        if self.mode == "p2p":
-            # the rows already sit in every replica; wait until all ranks' stores have landed
+        if self.mode in ("local", "p2p"):
+            return      # p2p: the rows already sit in every replica, completion is signalled on the device
+        if self.mode == "p2p-host":
             self.fit.sync()
             self.dist.barrier(group=self.group)
             return
@@ -190,6 +213,7 @@ class GpuBackend:
             w.wait()
 
     def factors(self):
+        self.finish()
         if self.mode == "nccl":
             k = self.k
             return self.A[:, :k].cpu().numpy(), self.B[:, :k].cpu().numpy()

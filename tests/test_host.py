@@ -183,7 +183,17 @@ def _gloo_worker(rank, world, port, case, q):
             before = M.copy()
             self._one_side(side, M, F, params, step)
             M[:lo] = before[:lo]; M[hi:] = before[hi:]
-            return 0
+            # tncg early stop (src/poismf.c:393-396): LOCAL rows with non-zeros that moved less than 1e-4
+            nz = np.diff(ptr2)[lo:hi] > 0
+            d = before[lo:hi] - M[lo:hi]
+            moved = np.zeros(hi - lo)
+            for c in range(d.shape[1]):                       # the reference's left-to-right dot
+                moved = moved + d[:, c] * d[:, c]
+            return int(((moved <= 1e-4) & nz).sum())
+        def allreduce_int(self, v):
+            t = torch.tensor([int(v)], dtype=torch.int64)
+            dist.all_reduce(t)
+            return int(t.item())
         def _one_side(self, side, M, F, params, step):
             import ctypes as C
             r = C.c_double
@@ -212,10 +222,12 @@ def _gloo_worker(rank, world, port, case, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["pg", "cg", "tncg"])
+@pytest.mark.parametrize("case", ["pg", "cg", "tncg", "tncg_reuse_stop"])
 def test_sharded_sweep_gloo_world2(case):
     """Two CPU ranks, each updating only its own nnz-balanced row/column range and exchanging
-    slices, reproduce the unsharded oracle bit for bit."""
+    slices, reproduce the unsharded oracle bit for bit — including tncg's early stop, whose count of
+    unchanged rows is summed over the ranks before it is compared with the dimension
+    (src/poismf.c:393-403, :606): with local counts the ranks would disagree on when to stop."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
