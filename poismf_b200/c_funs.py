@@ -94,7 +94,10 @@ def _predict_multiple(out, A, B, ix_u, ix_i, nthreads=1):
         raise MemoryError(_lib.last_error())
 
 
-def _call_topN(a_vec, B, include_ix, exclude_ix, top_n=10, output_score=False, nthreads=1):
+def _call_topN(a_vec, B, include_ix, exclude_ix, top_n=10, output_score=False, nthreads=1, check=False):
+    """poismf_c_wrapper.pxi:208-249.  Like the reference's wrapper the return code 2 (invalid arguments,
+    src/topN.c:124-128) is NOT turned into an exception — PoisMF.topN validates its arguments before the
+    call (poismf/__init__.py:933-975); `check=True` raises ValueError instead."""
     _lib.require_gpu()
     ixdt = np.uint64
     inc = np.ascontiguousarray(include_ix, dtype=ixdt)
@@ -110,7 +113,7 @@ def _call_topN(a_vec, B, include_ix, exclude_ix, top_n=10, output_score=False, n
         _lib.ptr(outp_ix), _lib.ptr(outp_score) if output_score else None, top_n, B.shape[0])
     if rc == 1:
         raise MemoryError(_lib.last_error())
-    if rc == 2:
+    if rc == 2 and check:
         raise ValueError("topN: invalid arguments")
     return outp_ix, outp_score
 

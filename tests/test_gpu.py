@@ -274,9 +274,10 @@ def test_topn_invalid_arguments_return_2():
     B = np.ones((10, 3)); a = np.ones(3)
     none = np.empty(0, np.uint64)
     with pytest.raises(ValueError):
-        c_funs._call_topN(a, B, none, none, top_n=0)
+        c_funs._call_topN(a, B, none, none, top_n=0, check=True)
     with pytest.raises(ValueError):
-        c_funs._call_topN(a, B, none, np.arange(6, dtype=np.uint64), top_n=5)
+        c_funs._call_topN(a, B, none, np.arange(6, dtype=np.uint64), top_n=5, check=True)
+    c_funs._call_topN(a, B, none, np.arange(6, dtype=np.uint64), top_n=5)     # the reference's wrapper ignores the code
 
 
 # ---------------------------------------------------------------- BASELINE full size (config #2)

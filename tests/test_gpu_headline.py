@@ -145,7 +145,7 @@ def test_benchmarked_mode_cg_f32_vs_reference(config):
     # `pip install poismf` compiles): against THAT build the per-row objective is unbiased ...
     for side in ("A", "B"):
         r = hs[f"{side}_dev_vs_fast"]
-        assert abs(r["median"]) <= 2e-5, (side, r)
+        assert r["median"] <= 2e-5 and abs(r["median"]) <= 1e-3, (side, r)      # never worse in the median
         assert r["worse_frac"] <= r["better_frac"] + 0.05, (side, r)
     # ... and against the strict (no-FMA, sequential) build it is no further away than the reference's
     # FMA build itself is (with limit_step the contracted update x + step*d leaves the limiting
