@@ -75,7 +75,7 @@ def build(force=False, verbose=False):
                     print(out)
     if force or jobs or _newer(LIB, objs):
         _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                     "-cudart", "shared"])
+                                                     "-cudart", "shared", "-ldl"])
     # host drop-in layer: the reference's own prototypes (real_t / sparse_ix variants)
     host_src = os.path.join(HOST, "poismf_host.c")
     inc = os.path.join(HERE, "..", "include")

@@ -159,8 +159,8 @@ __global__ void predict_pairs_kernel(const real* __restrict__ A, const real* __r
                                      size_t n, int k, int ldf, real* __restrict__ out)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const real* a = A + (size_t)ixA[i] * ldf;
-        const real* b = B + (size_t)ixB[i] * ldf;
+        const real* a = A + (ixA ? (size_t)ixA[i] : i) * ldf;       // no index arrays: row i of each (gathered) block
+        const real* b = B + (ixB ? (size_t)ixB[i] : i) * ldf;
         real acc = 0;
         for (int c = 0; c < k; c++) acc = add_rn(acc, mul_rn(a[c], b[c]));
         out[i] = acc;

@@ -706,3 +706,45 @@ def test_very_heavy_columns_streaming_clusters(dtype):
     assert run_device(csr, csc, A, B, "pg", kw) == 0
     gate = 1e-5 if dtype == np.float64 else 1e-3
     assert row_rel_err(A, Ar).max() <= gate and row_rel_err(B, Br).max() <= gate
+
+
+# ---------------------------------------------------------------- point queries (uploads per call)
+def test_topn_batch_rejects_invalid_ids():
+    """Ids outside the matrices, non-monotone offsets and users left with fewer than n_top items return 2
+    (ValueError), as the single-user entry does (src/topN.c:121-128) — nothing is read out of bounds."""
+    from poismf_b200 import c_funs
+    rng = np.random.default_rng(2)
+    A = np.ascontiguousarray(rng.gamma(1, 1, size=(20, 8)).astype(np.float32))
+    B = np.ascontiguousarray(rng.gamma(1, 1, size=(300, 8)).astype(np.float32))
+    ok_ptr = np.array([0, 2, 4], np.uint64); ok_ix = np.array([1, 5, 7, 9], np.uint64)
+    c_funs._topN_batch(A, B, users=np.array([0, 19], np.uint64), excl_ptr=ok_ptr, excl_ix=ok_ix, top_n=5)
+    with pytest.raises(ValueError):
+        c_funs._topN_batch(A, B, users=np.array([0, 20], np.uint64), top_n=5)
+    with pytest.raises(ValueError):
+        c_funs._topN_batch(A, B, users=np.array([0, 1], np.uint64), excl_ptr=ok_ptr, excl_ix=np.array([1, 5, 7, 300], np.uint64), top_n=5)
+    with pytest.raises(ValueError):
+        c_funs._topN_batch(A, B, users=np.array([0, 1], np.uint64), excl_ptr=np.array([0, 3, 2], np.uint64), excl_ix=ok_ix, top_n=5)
+    with pytest.raises(ValueError):
+        c_funs._topN_batch(A, B, users=np.array([0], np.uint64), excl_ptr=np.array([0, 298], np.uint64),
+                           excl_ix=np.arange(298, dtype=np.uint64), top_n=5)
+
+
+def test_resident_item_factors_between_topn_calls(monkeypatch):
+    """POISMF_B200_CACHE_FACTORS=1 keeps the padded item factors on the device for the next call on the same
+    array: same results as without, and an in-place edit of the array is noticed."""
+    from poismf_b200 import _lib, c_funs
+    rng = np.random.default_rng(4)
+    B = np.ascontiguousarray(rng.gamma(1, 1, size=(5000, 50)).astype(np.float32))
+    A = np.ascontiguousarray(rng.gamma(1, 1, size=(30, 50)).astype(np.float32))
+    none = np.empty(0, np.uint64)
+    want = [c_funs._call_topN(np.ascontiguousarray(A[u]), B, none, none, top_n=7, output_score=True) for u in range(5)]
+    monkeypatch.setenv("POISMF_B200_CACHE_FACTORS", "1")
+    for rep in range(2):
+        for u in range(5):
+            ix, sc = c_funs._call_topN(np.ascontiguousarray(A[u]), B, none, none, top_n=7, output_score=True)
+            assert np.array_equal(ix, want[u][0]) and np.array_equal(sc, want[u][1])
+    B *= 0.5                                                  # same pointer, new contents
+    ix, sc = c_funs._call_topN(np.ascontiguousarray(A[0]), B, none, none, top_n=7, output_score=True)
+    assert np.array_equal(sc, want[0][1] * 0.5)
+    monkeypatch.delenv("POISMF_B200_CACHE_FACTORS")
+    _lib.lib().pmf_b200_release_cache()
