@@ -116,6 +116,7 @@ struct DensePlan {
     float* sx = nullptr;
     float *p = nullptr, *q = nullptr, *dvec = nullptr, *gprev = nullptr, *dprev = nullptr, *gpart = nullptr, *lsp = nullptr;
     DenseScal* sc = nullptr;
+    int* tile_counters = nullptr;          // one per dots launch of a half-sweep
     std::vector<cudaEvent_t> ev;
     void release()
     {
@@ -470,6 +471,7 @@ template <class real> struct HandleT : pmf_b200_handle {
         if (grab(&D.gpart, (size_t)D.G * H * ldf * sizeof(float))) return 1;
         if (grab(&D.lsp, (size_t)D.nchunks * DN_TRIALS * sizeof(float))) return 1;
         if (grab(&D.sc, (size_t)H * sizeof(DenseScal))) return 1;
+        if (grab(&D.tile_counters, 64 * sizeof(int))) return 1;
         CK(cudaMemcpyAsync(tables, dn_i32.data(), dn_i32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(D.hbeg, dn_hbeg.data(), (size_t)H * sizeof(long long), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(D.q, 0, (size_t)nnzH * sizeof(float), st));
@@ -540,7 +542,10 @@ template <class real> struct HandleT : pmf_b200_handle {
         }
         const int hg = (D.H + 3) / 4;
         const int gd = (int)std::min<long long>(4 * num_sms, D.T);   // dots passes: four persistent CTAs per SM
+        CK(cudaMemsetAsync(D.tile_counters, 0, 64 * sizeof(int), st));
+        int n_dots = 0;
         dense_reset_kernel<<<(D.H + 127) / 128, 128, 0, st>>>(P);
+        P.tile_counter = D.tile_counters + (n_dots++ & 63);
         dense_walk_kernel<0><<<gd, DnWalk<0>::threads, smem_dots, st>>>(P);
         dense_ls_kernel<<<D.nchunks, 256, 0, st>>>(P, 0);
         dense_init_kernel<<<hg, 128, 0, st>>>(P);
@@ -549,6 +554,8 @@ template <class real> struct HandleT : pmf_b200_handle {
         for (long long it = 0; it < maxiter; it++) {
             dense_walk_kernel<2><<<D.G, DnWalk<2>::threads, smem_g, st>>>(P);
             dense_k_kernel<<<D.H, 256, 0, st>>>(P);
+            if ((n_dots & 63) == 0) CK(cudaMemsetAsync(D.tile_counters, 0, 64 * sizeof(int), st));   // all 64 used up
+            P.tile_counter = D.tile_counters + (n_dots++ & 63);
             dense_walk_kernel<1><<<gd, DnWalk<1>::threads, smem_dots, st>>>(P);
             dense_ls_kernel<<<D.nchunks, 256, 0, st>>>(P, 1);
             dense_choose_kernel<<<hg, 128, 0, st>>>(P);

@@ -91,6 +91,7 @@ struct DenseParams {
     float* gpart;                       // [G][H][ldf]
     float* lsp;                         // [nchunks][DN_TRIALS]
     DenseScal* sc;                      // [H]
+    int* tile_counter;                  // dots passes: tiles are handed out dynamically (zeroed before the launch)
     HalfSweepConsts<float> hc;
     float* peerM[7];
     int npeers;
@@ -151,7 +152,18 @@ __global__ void __launch_bounds__(DnWalk<MODE>::threads, DnWalk<MODE>::min_ctas)
     const unsigned clo = chunk_ok ? (unsigned)cl * 16u : 0u;          // lanes beyond the row read chunk 0 (and discard)
     float* out = MODE == 0 ? P.p : P.q;
     int nload = 0;
-    for (int tau = tau0; tau < tau1; tau++) {
+    __shared__ int next_tile;
+    for (int tau = tau0;; tau++) {
+        if (NBUF == 2) {
+            if (tau >= tau1) break;
+        } else {
+            // the dots passes accumulate nothing across tiles: tiles are drawn from a counter (no tail of idle CTAs)
+            if (threadIdx.x == 0) next_tile = atomicAdd(P.tile_counter, 1);
+            __syncthreads();
+            tau = next_tile;
+            __syncthreads();
+            if (tau >= P.T) break;
+        }
         const int n0 = P.seg_ptr[(size_t)tau * H], n1 = P.seg_ptr[(size_t)(tau + 1) * H];
         const int nb = n1 - n0;
         int b, phase;
@@ -187,28 +199,53 @@ __global__ void __launch_bounds__(DnWalk<MODE>::threads, DnWalk<MODE>::min_ctas)
             first = false;
         };
         bool waited = false;
+        // Entry loads run two batches ahead, the loads that depend on them (row state, p, q, value) one batch
+        // ahead, so that their latency is covered by the visits of the current batch.
+        // lane j of the group loads entry j of a batch.  Beyond the group's range its own last entry (for an
+        // empty range: the tile's last entry) stands in with a zero coefficient / no output, so that the
+        // inner loop has nothing to test and no heavy row gets a second writer.
+        struct Dep { int active; float step, pt, qt, x; };
+        const int last_valid = (r1 > r0 ? r1 : n1) - 1;
+        auto load_ent = [&](int u) {
+            const int mine = r0 + u + cl;
+            return __ldg(P.ent + ((mine < r1 && u < m) ? mine : last_valid));
+        };
+        auto load_dep = [&](const uint2& e, int u) {
+            Dep d;
+            const DenseScal& S = P.sc[e.x & 0xffffu];
+            d.active = S.active;
+            d.step = 0.f; d.pt = 1.f; d.qt = 0.f; d.x = 0.f;
+            if (MODE == 2) {
+                const int mine = r0 + u + cl;
+                d.step = S.step_applied;
+                d.pt = P.p[e.y];
+                d.qt = P.q[e.y];
+                d.x = __ldg(P.sx + ((mine < r1 && u < m) ? mine : last_valid));
+            }
+            return d;
+        };
+        uint2 e0 = make_uint2(0u, 0u), e1 = e0;
+        Dep d0 = {};
+        if (nb > 0) { e0 = load_ent(0); d0 = load_dep(e0, 0); e1 = load_ent(16); }
         for (int u = 0; u < m && nb > 0; u += 16) {
-            // lane j of the group loads entry j of this batch.  Beyond the group's range its own last entry
-            // (for an empty range: the tile's last entry) stands in with a zero coefficient / no output, so
-            // that the inner loop has nothing to test and no heavy row gets a second writer.
+            const uint2 e = e0;
+            const Dep d = d0;
+            e0 = e1;
+            if (u + 16 < m) d0 = load_dep(e0, u + 16);
+            if (u + 32 < m) e1 = load_ent(u + 32);
             const int mine = r0 + u + cl;
             const bool real = mine < r1;
-            const uint2 e = __ldg(P.ent + (real ? mine : (r1 > r0 ? r1 : n1) - 1));
             const unsigned off = e.x >> 16;
             const int h = (int)(e.x & 0xffffu);
             unsigned cp = e.y;
             float c = 0.f;
-            {
-                const DenseScal& S = P.sc[h];
-                if (MODE == 2) {
-                    if (real && S.active) {
-                        const float step = S.step_applied;
-                        float pt = P.p[cp];
-                        if (step != 0.f) { pt = fmaf(step, P.q[cp], pt); P.p[cp] = pt; }
-                        c = -__ldg(P.sx + mine) / pt;
-                    }
-                } else if (!real || !S.active) cp = 0xffffffffu;
-            }
+            if (MODE == 2) {
+                if (real && d.active) {
+                    float pt = d.pt;
+                    if (d.step != 0.f) { pt = fmaf(d.step, d.qt, pt); P.p[cp] = pt; }
+                    c = -d.x / pt;
+                }
+            } else if (!real || !d.active) cp = 0xffffffffu;
             if (!waited) { dn_mbar_wait(&bar[b], (unsigned)phase); waited = true; }
             if (MODE == 2) {
 #pragma unroll 4

@@ -164,9 +164,12 @@ template <int NC, int NW> PMF_DEVINL void rt_read_dir(const RtShared<NW>& sh, fl
 
 // resident CTAs per SM the kernels are compiled for: 16 warps per SM when a lane holds 4 tile rows
 // (128 registers), 20 with fewer
+#ifndef PMF_RT_WARPS64
+#define PMF_RT_WARPS64 20
+#endif
 template <int NC, int TPL, int NW> struct RtCfg {
     static constexpr int tile_regs = 4 * NC * TPL;
-    static constexpr int warps_per_sm = tile_regs >= 64 ? 16 : (tile_regs >= 48 ? 20 : 24);
+    static constexpr int warps_per_sm = tile_regs >= 64 ? PMF_RT_WARPS64 : (tile_regs >= 48 ? 20 : 24);
     static constexpr int min_ctas = warps_per_sm / NW < 1 ? 1 : warps_per_sm / NW;
 };
 
