@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -351,7 +351,6 @@ def main():
         ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = L.pmf_b200_kernel_launches() - launches0
     # second pass over the same K sweeps with per-launch CUDA events (bins run one after the
     # other on the launching stream here; in the timed pass above they overlap on side streams)
@@ -366,6 +365,7 @@ def main():
         pe1.record(stream)
     barrier()
     ms_profiled_pass = pe0.elapsed_time(pe1)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the timed pass and the per-launch pass
     prof = profiler.get_profile()
     profiler.set_profiling(False)
     if dist is not None:
@@ -405,7 +405,7 @@ def main():
                 "kernel_avg_ms": avg_ms, "kernel_share_of_step": top["ms"] / max(ms_profiled_pass, 1e-9),
                 "serialized_ms_per_step": ms_profiled_pass / args.steps,
                 "sweep_algorithmic_GBps": sweep_bytes / (ms_step / 1e3) / 1e9,
-                "sweep_frac_of_peak": sweep_bytes / (ms_step / 1e3) / 1e9 / peak,
+                "sweep_frac_of_peak": sweep_bytes / (ms_step / 1e3) / 1e9 / peak / max(args.gpus, 1),   # per GPU
                 "bins": [{"side": p["side"], "team": team_name(p["block_team"]), "cap": p["cap"],
                           "rows": p["nrows"], "nnz": p["nnz"], "ms_per_sweep": p["ms"] / args.steps,
                           "GBps": (p["nnz"] * (k * s + s + 4) + p["nrows"] * (2 * k * s + 8)) / max(p["ms"] / args.steps, 1e-9) / 1e6}
@@ -501,17 +501,19 @@ def main():
         from poismf_b200.sharding import ShardedSweep
         ts = []
         h2d = d2h = 0
+        outA, outB = np.empty_like(A0), np.empty_like(B0)
         for it in range(4):
             dist.barrier()
             t0 = time.perf_counter()
             be.load(csr, csc, A0, B0)
             ShardedSweep(be, dimA, dimB, np.float32).run(params)
-            be.factors()
+            be.factors(root=0, out=(outA, outB))
+            dist.barrier()
             dt = time.perf_counter() - t0
             a0, a1 = be.rangesA[rank]; b0, b1 = be.rangesB[rank]
-            h2d = (A0.nbytes + B0.nbytes + int(csr[1][a1] - csr[1][a0]) * 12 + int(csc[1][b1] - csc[1][b0]) * 12
+            h2d = ((A0.nbytes + B0.nbytes) // world + int(csr[1][a1] - csr[1][a0]) * 12 + int(csc[1][b1] - csc[1][b0]) * 12
                    + (a1 - a0 + b1 - b0) * 8)
-            d2h = A0.nbytes + B0.nbytes
+            d2h = A0.nbytes + B0.nbytes if rank == 0 else 0
             if it > 0:
                 ts.append(dt)
         t = torch.tensor([float(np.mean(ts))], device="cuda", dtype=torch.float64)
@@ -519,8 +521,9 @@ def main():
         e_ms = 1e3 * float(t.item())
         e2e = {"value": nnz / (e_ms / 1e3), "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e_ms, "steps": len(ts),
-               "call": "GpuBackend.load + ShardedSweep.run(numiter=1) + factors() on a persistent backend: per-rank shard "
-                       "upload, plan, sweep with the fused exchange, download (max over ranks)"}
+               "call": "GpuBackend.load + ShardedSweep.run(numiter=1) + factors(root=0) on a persistent backend: every rank "
+                       "uploads its matrix shard and 1/N of the initial factors (stored into all replicas over NVLink), plan, "
+                       "sweep with the fused exchange, rank 0 reads A and B back (max over ranks; bytes are per rank)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

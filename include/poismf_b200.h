@@ -107,6 +107,10 @@ int pmf_b200_sync(pmf_b200_handle* h);
 int pmf_b200_ipc_export(pmf_b200_handle* h, int which /*0=A,1=B,2=epoch slots*/, void* handle_out);
 /* handles: n_ranks x 64 bytes in rank order (own entry ignored).  n_ranks <= 8. */
 int pmf_b200_ipc_import(pmf_b200_handle* h, int which, const void* handles, int n_ranks, int self_rank);
+/* Rows [row_begin, row_begin + n_rows) of A (which = 0) or B (1), k reals per row in host memory, into the
+ * own replica and — over NVLink, through the mappings imported above — into every peer's: the ranks of a
+ * sharded fit each upload 1/N of the initial factors (poismf/__init__.py:419-425 draws them on the host). */
+int pmf_b200_set_factor_rows(pmf_b200_handle* h, int which, const void* rows, size_t row_begin, size_t n_rows);
 
 /* Per-launch device timing of the row kernels (CUDA events on the handle's stream),
  * for bench.py's roofline line: one entry per (side, row bin). */

@@ -22,7 +22,7 @@ FLAG_STRICT, FLAG_NO_CACHED, FLAG_NO_LOCKSTEP = 1, 2, 4
 SYMBOLS = [
     "pmf_b200_device_count", "pmf_b200_last_error", "pmf_b200_kernel_launches",
     "pmf_b200_create", "pmf_b200_destroy", "pmf_b200_ldf", "pmf_b200_set_matrix",
-    "pmf_b200_set_factors", "pmf_b200_get_factors", "pmf_b200_bind_factors", "pmf_b200_factor_ptr",
+    "pmf_b200_set_factors", "pmf_b200_get_factors", "pmf_b200_bind_factors", "pmf_b200_set_factor_rows", "pmf_b200_factor_ptr",
     "pmf_b200_set_stream", "pmf_b200_sweeps", "pmf_b200_half_sweep", "pmf_b200_sync",
     "pmf_b200_set_profiling", "pmf_b200_get_profile", "pmf_b200_ipc_export", "pmf_b200_ipc_import",
     "pmf_b200_run_poismf", "pmf_b200_factors_multiple", "pmf_b200_factors_single", "pmf_b200_predict_multiple", "pmf_b200_topN", "pmf_b200_topN_batch", "pmf_b200_topN_stats",
@@ -66,6 +66,8 @@ def lib():
     L.pmf_b200_set_factors.argtypes = [vp, vp, vp]
     L.pmf_b200_get_factors.argtypes = [vp, vp, vp]
     L.pmf_b200_bind_factors.argtypes = [vp, vp, vp]
+    L.pmf_b200_set_factor_rows.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t]
+    L.pmf_b200_set_factor_rows.restype = C.c_int
     L.pmf_b200_factor_ptr.argtypes = [vp, i]
     L.pmf_b200_factor_ptr.restype = vp
     L.pmf_b200_set_stream.argtypes = [vp, vp]

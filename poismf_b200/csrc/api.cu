@@ -177,6 +177,7 @@ struct pmf_b200_handle {
     virtual int set_factors(const void* A, const void* B) = 0;
     virtual int get_factors(void* A, void* B) = 0;
     virtual int bind_factors(void* A, void* B) = 0;
+    virtual int set_factor_rows(int which, const void* host, size_t row_begin, size_t n_rows) = 0;
     virtual void* factor_ptr(int which) = 0;
     virtual int half_sweep(int side, const pmf_b200_params& p, double step, double cdiv,
                            unsigned long long* n_unchanged) = 0;
@@ -390,6 +391,21 @@ template <class real> struct HandleT : pmf_b200_handle {
         int rc = 0;
         if (Ah) rc = copy_in(A, Ah, dimA, stream);
         if (Bh && !rc) rc = copy_in(B, Bh, dimB, stream);
+        return sync_all() || rc;
+    }
+    // rows [row_begin, row_begin + n_rows) of A (which = 0) or B (1) from host memory into the own replica AND,
+    // over NVLink, into every peer's: a sharded fit uploads each factor row once per box instead of once per GPU
+    int set_factor_rows(int which, const void* host, size_t row_begin, size_t n_rows) override
+    {
+        CK(cudaSetDevice(device));
+        if (which != 0 && which != 1) return fail("set_factor_rows: which must be 0 (A) or 1 (B)");
+        const size_t dim = which == 0 ? dimA : dimB;
+        if (row_begin + n_rows > dim) return fail("set_factor_rows: row range exceeds the dimension");
+        real* M = (which == 0 ? A : B) + row_begin * (size_t)ldf;
+        int rc = n_rows ? copy_in(M, host, n_rows, stream) : 0;
+        for (int q = 0; q < npeers[which] && !rc && n_rows; q++)
+            CK(cudaMemcpyAsync(peer[which][q] + row_begin * (size_t)ldf, M, n_rows * (size_t)ldf * sizeof(real),
+                               cudaMemcpyDeviceToDevice, stream));
         return sync_all() || rc;
     }
     int get_factors(void* Ah, void* Bh) override
@@ -731,6 +747,12 @@ template <class real> struct HandleT : pmf_b200_handle {
             }
             std::sort(cand.begin(), cand.end());          // heaviest first, ties by row id
             if (cand.size() > hmax) cand.resize(hmax);
+            // the lock-step phase costs ~30 launches per half-sweep whatever its size: below ~250k non-zeros the
+            // per-row cluster teams are cheaper (small shards of a multi-GPU fit, the user side of config #2)
+            long long dense_nnz = 0, dense_min_total = 250000;
+            for (auto& c : cand) dense_nnz -= c.first;
+            if (const char* e = getenv("POISMF_B200_DENSE_MIN_TOTAL")) dense_min_total = atoll(e);
+            if (dense_nnz < dense_min_total) cand.clear();
             if (!cand.empty()) {
                 std::vector<int> hrows;
                 for (auto& c : cand) hrows.push_back(c.second);
@@ -1391,6 +1413,10 @@ extern "C" int pmf_b200_set_matrix(pmf_b200_handle* h, int side, const void* val
 extern "C" int pmf_b200_set_factors(pmf_b200_handle* h, const void* A, const void* B) { return h->set_factors(A, B); }
 extern "C" int pmf_b200_get_factors(pmf_b200_handle* h, void* A, void* B) { return h->get_factors(A, B); }
 extern "C" int pmf_b200_bind_factors(pmf_b200_handle* h, void* A, void* B) { return h->bind_factors(A, B); }
+extern "C" int pmf_b200_set_factor_rows(pmf_b200_handle* h, int which, const void* rows, size_t row_begin, size_t n_rows)
+{
+    return h->set_factor_rows(which, rows, row_begin, n_rows);
+}
 extern "C" void* pmf_b200_factor_ptr(pmf_b200_handle* h, int which) { return h->factor_ptr(which); }
 extern "C" int pmf_b200_set_stream(pmf_b200_handle* h, void* s)
 {

@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(128) dense_init_kernel(const DenseParams P)
     if (h >= P.H) return;
     DenseScal& S = P.sc[h];
     float ls = 0.f;
-    for (int ch = P.chunk_ptr[h]; ch < P.chunk_ptr[h + 1]; ch++) ls += P.lsp[(size_t)ch * DN_TRIALS];   // fixed order
+    for (int ch = P.chunk_ptr[h] + lane; ch < P.chunk_ptr[h + 1]; ch += 32) ls += P.lsp[(size_t)ch * DN_TRIALS];
+    ls = warp_sum(ls);                                                                              // fixed order
     const float* x = P.M + (size_t)P.hrow[h] * P.ldf;
     float reg = 0.f, sq = 0.f;
     for (int i = lane; i < P.k; i += 32) { const float xi = x[i]; reg = fmaf(P.csum[i], xi, reg); sq = fmaf(xi, xi, sq); }
@@ -396,13 +397,20 @@ __global__ void __launch_bounds__(256) dense_k_kernel(const DenseParams P)
     if (!S.active) return;
     const int k = P.k, ldf = P.ldf;
     {
-        float s0 = 0.f, s1 = 0.f;
-        for (int b = warp; b < P.G; b += 8) {
+        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+        int b = warp;
+        for (; b + 8 < P.G; b += 16) {                       // two partials in flight per lane (fixed pairing)
+            const float* gp = P.gpart + ((size_t)b * P.H + h) * ldf;
+            const float* gq = P.gpart + ((size_t)(b + 8) * P.H + h) * ldf;
+            if (lane < ldf) { s0 += gp[lane]; t0 += gq[lane]; }
+            if (lane + 32 < ldf) { s1 += gp[lane + 32]; t1 += gq[lane + 32]; }
+        }
+        for (; b < P.G; b += 8) {
             const float* gp = P.gpart + ((size_t)b * P.H + h) * ldf;
             if (lane < ldf) s0 += gp[lane];
             if (lane + 32 < ldf) s1 += gp[lane + 32];
         }
-        part[warp][lane] = s0; part[warp][lane + 32] = s1;
+        part[warp][lane] = s0 + t0; part[warp][lane + 32] = s1 + t1;
     }
     __syncthreads();
     if (warp != 0) return;
@@ -469,10 +477,18 @@ __global__ void __launch_bounds__(128) dense_choose_kernel(const DenseParams P)
     const float c_ls = 0.01f;
     const float fcur = S.fcur, regx = S.regx, dsq = S.dsq, lin = S.lin, l2dd = hc.l2 * S.dsq;
     auto freg = [&](float sj) { return fmaf(sj, fmaf(sj, l2dd, lin), regx); };
-    // lane j: sum of the line-search pass for trial j (fixed order over the row's chunks), its objective
+    // lane j: sum of the line-search pass for trial j, its objective.  The row's chunk partials are summed by
+    // all 32 lanes (lane = chunk mod 32, then a shuffle tree): a fixed order, whatever the launch
     float tot = 0.f;
-    if (lane < DN_TRIALS)
-        for (int ch = P.chunk_ptr[h]; ch < P.chunk_ptr[h + 1]; ch++) tot += P.lsp[(size_t)ch * DN_TRIALS + lane];
+    {
+        const int c0 = P.chunk_ptr[h], c1 = P.chunk_ptr[h + 1];
+        for (int j = 0; j < DN_TRIALS; j++) {
+            float v = 0.f;
+            for (int ch = c0 + lane; ch < c1; ch += 32) v += P.lsp[(size_t)ch * DN_TRIALS + j];
+            v = warp_sum(v);
+            if (lane == j) tot = v;
+        }
+    }
     const float sj = lane < DN_TRIALS ? S.steps[lane] : 0.f;
     const float fj = freg(sj) - tot * hc.w;
     const bool okj = lane < DN_TRIALS && !is_bad(fj) && fj <= fcur - c_ls * sj * dsq;

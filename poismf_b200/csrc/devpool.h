@@ -135,22 +135,27 @@ public:
     }
 
 private:
+    // cap on the idle bytes kept per device: POISMF_B200_POOL_MB, else a quarter of THAT device's memory
+    // (co-resident allocators such as PyTorch's need the rest; pmf_b200_release_cache() empties the pool)
     size_t cap(int dev)     // mu_ held
     {
-        if (cap_ >= 0) return (size_t)cap_;
+        auto it = cap_.find(dev);
+        if (it != cap_.end()) return it->second;
+        size_t c = 0;
         if (const char* e = getenv("POISMF_B200_POOL_MB")) {
-            cap_ = (long long)(atof(e) * 1048576.0);
-            if (cap_ < 0) cap_ = 0;
-            return (size_t)cap_;
+            const double mb = atof(e);
+            c = mb > 0 ? (size_t)(mb * 1048576.0) : 0;
+        } else {
+            size_t fr = 0, total = 0;
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cur != dev) cudaSetDevice(dev);
+            if (cudaMemGetInfo(&fr, &total) != cudaSuccess) { cudaGetLastError(); total = 0; }
+            if (cur != dev) cudaSetDevice(cur);
+            c = total / 4;
         }
-        size_t fr = 0, total = 0;
-        int cur = 0;
-        cudaGetDevice(&cur);
-        if (cur != dev) cudaSetDevice(dev);
-        if (cudaMemGetInfo(&fr, &total) != cudaSuccess) { cudaGetLastError(); total = 0; }
-        if (cur != dev) cudaSetDevice(cur);
-        cap_ = (long long)(total / 2);
-        return (size_t)cap_;
+        cap_[dev] = c;
+        return c;
     }
 
     std::mutex mu_;
@@ -158,7 +163,7 @@ private:
     struct PtrHash { size_t operator()(const void* p) const { return std::hash<const void*>()(p); } };
     std::unordered_map<void*, std::pair<int, size_t>, PtrHash> live_;
     size_t idle_bytes_ = 0;
-    long long cap_ = -1;
+    std::unordered_map<int, size_t> cap_;
 };
 
 template <class T> static inline cudaError_t dmalloc(T** out, size_t bytes) { return DevPool::get().alloc((void**)out, bytes); }

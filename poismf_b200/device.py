@@ -60,6 +60,11 @@ class DeviceFit:
     def bind_factors(self, A_dev_ptr=None, B_dev_ptr=None):
         self._ck(self.L.pmf_b200_bind_factors(self.h, A_dev_ptr, B_dev_ptr))
 
+    def set_factor_rows(self, which, rows, row_begin):
+        """Rows [row_begin, row_begin + len(rows)) of A (0) / B (1) into this replica and every peer's."""
+        assert rows.dtype == self.dtype and rows.flags.c_contiguous
+        self._ck(self.L.pmf_b200_set_factor_rows(self.h, which, _lib.ptr(rows), row_begin, rows.shape[0]))
+
     def factor_ptr(self, which):
         return self.L.pmf_b200_factor_ptr(self.h, which)
 

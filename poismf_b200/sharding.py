@@ -169,6 +169,12 @@ class GpuBackend:
         if self.mode == "nccl":
             self.A[:, :self.k].copy_(self.torch.from_numpy(A0))
             self.B[:, :self.k].copy_(self.torch.from_numpy(B0))
+        elif self.mode in ("p2p", "p2p-host"):
+            # every rank uploads 1/N of the rows and stores them into all replicas over NVLink: each factor
+            # row crosses PCIe once per box, not once per GPU
+            for which, M in ((0, A0), (1, B0)):
+                lo, hi = user_ranges(M.shape[0], self.world)[self.rank]
+                self.fit.set_factor_rows(which, np.ascontiguousarray(M[lo:hi]), lo)
         else:
             self.fit.set_factors(A0, B0)
         self.torch.cuda.synchronize(self.dev)
@@ -212,12 +218,16 @@ class GpuBackend:
         for w in works:
             w.wait()
 
-    def factors(self):
+    def factors(self, root=None, out=None):
+        """The fitted factors as host arrays.  Every rank's replica holds the same bits; with `root` set only
+        that rank reads them back (the others return None) — the process that asked for the fit."""
         self.finish()
+        if root is not None and self.rank != root:
+            return None
         if self.mode == "nccl":
             k = self.k
             return self.A[:, :k].cpu().numpy(), self.B[:, :k].cpu().numpy()
-        return self.fit.get_factors()
+        return self.fit.get_factors(*(out or (None, None)))
 
 
 def user_ranges(n_users, nparts):
