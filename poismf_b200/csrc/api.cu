@@ -1891,6 +1891,12 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             if (neg) use_tc = false;      // the TF32 error bound below assumes non-negative factors
         }
         const size_t ntiles = (n + tc::TN - 1) / tc::TN, ngroups = (n + tc::GROUP - 1) / tc::GROUP;
+        int num_sms = 148;
+        {
+            int dev = 0;
+            CK(cudaGetDevice(&dev));
+            CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
         if (use_tc && ngroups >= (size_t)2 * M_cand && !getenv("POISMF_B200_TOPN_SORT")) {
             // ---- fused select (topn_tc.cuh): no score matrix; two passes over the tensor-core tiles ----
             const size_t words = ntiles * 4;     // exclusion bitmap: 128 bits per tile and user
@@ -1951,14 +1957,36 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                     o.gmax = gmax; o.ngroups = ngroups; o.tau = tau;
                     o.cand_sc = cand_sc; o.cand_id = cand_id; o.cand_cnt = cand_cnt;
                     const dim3 tgrid((unsigned)ntiles, (unsigned)((m + tc::TM - 1) / tc::TM));
-                    tc::score_tiles_tf32_kernel<tc::MODE_GROUPMAX><<<tgrid, 128, (size_t)kpad * 1024>>>(
-                        (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
+                    // pipelined scorer (persistent CTAs, TMA operands, two TMEM accumulators) unless disabled
+                    CUtensorMap mapA, mapB;
+                    const bool piped = !getenv("POISMF_B200_TOPN_NOPIPE") &&
+                                       tc::make_operand_map(&mapA, (const float*)dAsel, m, ldf) == 0 &&
+                                       tc::make_operand_map(&mapB, (const float*)dB, n, ldf) == 0;
+                    const unsigned ut = (unsigned)((m + tc::PIPE_UT * tc::TM - 1) / (tc::PIPE_UT * tc::TM));   // CTAs along the users
+                    // one CTA per SM (shared memory): at most one wave of CTAs, each walking a long run of item tiles
+                    const unsigned chunks = (unsigned)std::max<size_t>(1, std::min<size_t>((ntiles + 7) / 8, (size_t)num_sms / ut));
+                    const int tiles_per_cta = (int)((ntiles + chunks - 1) / chunks);
+                    const size_t pipe_smem = (size_t)(tc::PIPE_UT + tc::PIPE_STAGES) * ((kpad + tc::PIPE_BOXK - 1) / tc::PIPE_BOXK) * 16384;
+                    if (piped) {
+                        CK(cudaFuncSetAttribute(tc::score_pipe_tf32_kernel<tc::MODE_GROUPMAX>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+                        CK(cudaFuncSetAttribute(tc::score_pipe_tf32_kernel<tc::MODE_EMIT>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+                        tc::score_pipe_tf32_kernel<tc::MODE_GROUPMAX><<<dim3(chunks, ut), tc::PIPE_THREADS, pipe_smem>>>(
+                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, o);
+                    } else
+                        tc::score_tiles_tf32_kernel<tc::MODE_GROUPMAX><<<tgrid, 128, (size_t)kpad * 1024>>>(
+                            (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
                     LAUNCHED();
                     tc::select_threshold_kernel<<<(unsigned)m, 256>>>(gmax, ngroups, M_cand, tau);
                     LAUNCHED();
                     CK(cudaMemsetAsync(cand_cnt, 0, m * sizeof(int)));
-                    tc::score_tiles_tf32_kernel<tc::MODE_EMIT><<<tgrid, 128, (size_t)kpad * 1024>>>(
-                        (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
+                    if (piped)
+                        tc::score_pipe_tf32_kernel<tc::MODE_EMIT><<<dim3(chunks, ut), tc::PIPE_THREADS, pipe_smem>>>(
+                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, o);
+                    else
+                        tc::score_tiles_tf32_kernel<tc::MODE_EMIT><<<tgrid, 128, (size_t)kpad * 1024>>>(
+                            (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
                     LAUNCHED();
                     tc::sort_candidates_kernel<<<(unsigned)m, 512>>>(cand_sc, cand_id, cand_cnt, top_sc, top_id, d_ovf);
                     LAUNCHED();

@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) dense_k_kernel(const DenseParams P)
         float sj = m;
 #pragma unroll
         for (int j = 0; j < DN_TRIALS; j++) { S.steps[j] = sj; sj *= 0.25f; }
-        if (fabs((double)gd) <= (double)1e-2f) S.active = 0;                                  // :264-269
+        if (fabsf(gd) <= 1e-2f) S.active = 0;                                                 // :264-269
     }
 }
 

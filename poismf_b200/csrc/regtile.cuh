@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32 * NW, RtCfg<NC, TPL, NW>::min_ctas) rows_re
                 }
                 team_sync();                 // (also: the previous readers of dsh are past their tile pass)
                 const float gd = sh.ksc[0], dsq = sh.ksc[1], gg = sh.ksc[2], lin = sh.ksc[3], smax = sh.ksc[4];
-                if (fabs((double)gd) <= (double)tol) break;                                  // :264-269
+                if (fabsf(gd) <= tol) break;                                                 // :264-269 (floats compare alike in double)
                 publish(dn);
                 team_sync();
                 rt_read_dir<NC, NW>(sh, vd, ig);

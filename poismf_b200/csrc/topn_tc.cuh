@@ -28,6 +28,7 @@
 // then the (<= 4096) candidates are ordered by (score desc, id asc) and the best M go to the exact
 // re-scoring as before.  Excluded items are masked in the epilogue from a per-user bitmap.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace pmf {
@@ -235,6 +236,280 @@ __global__ void __launch_bounds__(128) score_tiles_tf32_kernel(const float* __re
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TN) : "memory");
+}
+
+// ---- the pipelined scorer (r2): persistent CTAs, operands by TMA, accumulators double-buffered in TMEM ------
+// One CTA keeps TWO user tiles (256 users: the A operands, loaded once) and walks a contiguous range of item
+// tiles; every item tile brought on chip is used by both (half the L2 -> SM traffic of one tile per CTA).
+// Operands arrive by TMA (`cp.async.bulk.tensor.2d`, SASS UTMALDG): the factor matrices are described to the
+// TMA unit as 2-D tensors (k floats x rows) and fetched in boxes of 32 floats x 128 rows with the 128-byte
+// swizzle, i.e. whole 128-byte lines of 128 factor rows per request, landing in the K-major SWIZZLE_128B
+// layout the tensor core reads (descriptor: 8-row groups 1024 bytes apart, start address advanced by 32 bytes
+// per K = 8 step inside the swizzle atom); rows beyond the matrix and floats beyond k are zero-filled by the
+// TMA unit.  Item tiles go through a ring of PIPE_STAGES shared-memory stages guarded by mbarriers (expect_tx /
+// complete_tx); the accumulators of consecutive item tiles alternate between two TMEM buffers of 2 x 128
+// columns, so the epilogue of tile i-1 (TMEM -> registers -> group maxima / candidates) runs while the tensor
+// core works on tile i:
+// Warp roles (320 threads), coupled only through mbarriers:
+//     warp 9 (one lane) : for each tile: wait stage_free[s] -> expect_tx + TMA boxes -> full[s]
+//     warp 8 (one lane) : wait full[s], wait tmem_free[b] -> 2 x (k/8) tcgen05.mma into buffer b
+//                         -> tcgen05.commit to stage_free[s] and to mma_done[b]
+//     warps 0..7        : wait mma_done[b] -> TMEM -> registers (arrive on tmem_free[b] as soon as the last load
+//                         has landed) -> group maxima / candidates
+constexpr int PIPE_STAGES = 3;
+constexpr int PIPE_UT = 2;           // user tiles per CTA
+constexpr int PIPE_BOXK = 32;        // floats per TMA box along k (128 bytes: the swizzle span)
+constexpr int PIPE_THREADS = 320;    // 8 epilogue warps, the MMA warp, the TMA warp
+
+// TMEM -> registers without the wait, and the wait carrying the registers as operands (so that no use of them can
+// be scheduled above it): the load of the next 32 columns is in flight while the current ones are reduced
+PMF_DEVINL void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+PMF_DEVINL void tmem_ld_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+
+PMF_DEVINL void pipe_wait(uint64_t* bar, uint32_t phase)
+{
+    unsigned ok, spins = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();        // a lost copy must not hang the device
+    } while (!ok);
+}
+PMF_DEVINL void pipe_expect(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PMF_DEVINL void tma_box(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// K-major SWIZZLE_128B operand: rows 128 bytes apart, 8-row groups 1024 bytes apart (SBO), LBO unused (1),
+// descriptor version 1, layout type 2 (sm_100 encoding)
+PMF_DEVINL uint64_t make_smem_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// grid = (item-tile chunks, pairs of user tiles), PIPE_THREADS threads, dynamic shared memory
+// (PIPE_UT + PIPE_STAGES) * nbox * 16 KB with nbox = ceil(kpad / 32).
+// Epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (its quarter; = tile rows = users) of user tile w / 4.
+template <int MODE>
+__global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB, int U, size_t n,
+                                                              int kpad, int tiles_per_cta, TileOut out)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[PIPE_STAGES], stage_free[PIPE_STAGES], mma_done[2], tmem_free[2], a_full;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nbox = (kpad + PIPE_BOXK - 1) / PIPE_BOXK;
+    const uint32_t box_bytes = (uint32_t)TM * PIPE_BOXK * 4u;          // 16 KB
+    const uint32_t tile_bytes = (uint32_t)nbox * box_bytes;
+    unsigned char* sA = smem_raw;
+    unsigned char* sB = smem_raw + (size_t)PIPE_UT * tile_bytes;
+    const int u00 = blockIdx.y * (PIPE_UT * TM);
+    const size_t ntiles = (n + TN - 1) / TN;
+    const size_t t0 = (size_t)blockIdx.x * tiles_per_cta;
+    const int nt = t0 < ntiles ? (int)((ntiles - t0) < (size_t)tiles_per_cta ? (ntiles - t0) : (size_t)tiles_per_cta) : 0;
+
+    if (warp == 0) {   // two buffers of PIPE_UT accumulators of 128 columns: all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)(2 * PIPE_UT * TN))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(&a_full, 1);
+        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&stage_free[s], 1); }
+        mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+        mbar_init(&tmem_free[0], 8); mbar_init(&tmem_free[1], 8);      // one arrival per epilogue warp
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    constexpr uint32_t idesc = make_idesc_tf32(TM, TN);
+    if (warp == 9) {                 // ---- TMA producer ----
+        if (lane == 0 && nt > 0) {
+            pipe_expect(&a_full, PIPE_UT * tile_bytes);
+            for (int ut = 0; ut < PIPE_UT; ut++)
+                for (int bx = 0; bx < nbox; bx++)
+                    tma_box(sA + (size_t)ut * tile_bytes + (size_t)bx * box_bytes, &mapA, bx * PIPE_BOXK, u00 + ut * TM, &a_full);
+            for (int i = 0; i < nt; i++) {
+                const int s = i % PIPE_STAGES;
+                if (i >= PIPE_STAGES) pipe_wait(&stage_free[s], (uint32_t)((i / PIPE_STAGES - 1) & 1));
+                pipe_expect(&full[s], tile_bytes);
+                for (int bx = 0; bx < nbox; bx++)
+                    tma_box(sB + (size_t)s * tile_bytes + (size_t)bx * box_bytes, &mapB, bx * PIPE_BOXK, (int)((t0 + i) * TN), &full[s]);
+            }
+        }
+    } else if (warp == 8) {          // ---- MMA issuer ----
+        if (lane == 0 && nt > 0) {
+            const uint32_t a0 = smem_u32(sA), b00 = smem_u32(sB);
+            pipe_wait(&a_full, 0);
+            for (int i = 0; i < nt; i++) {
+                const int s = i % PIPE_STAGES, b = i & 1;
+                pipe_wait(&full[s], (uint32_t)((i / PIPE_STAGES) & 1));
+                if (i >= 2) pipe_wait(&tmem_free[b], (uint32_t)(((i >> 1) - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t db0 = make_smem_desc_sw128(b00 + (uint32_t)s * tile_bytes);
+                for (int ut = 0; ut < PIPE_UT; ut++) {
+                    const uint64_t da0 = make_smem_desc_sw128(a0 + (uint32_t)ut * tile_bytes);
+                    const uint32_t acc = tmem + (uint32_t)((b * PIPE_UT + ut) * TN);
+                    for (int kb = 0; kb < kpad / 8; kb++) {   // K = 8 (32 bytes inside the swizzle atom) per instruction
+                        const uint64_t koff = (uint64_t)(((uint32_t)(kb >> 2) * box_bytes + (uint32_t)(kb & 3) * 32u) >> 4);
+                        umma_tf32(acc, da0 + koff, db0 + koff, idesc, kb > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&stage_free[s]);
+                umma_commit(&mma_done[b]);
+            }
+        }
+    } else {                         // ---- epilogue warps ----
+    const int quarter = warp & 3, ut_mine = warp >> 2;       // TMEM lane quarter, user tile
+    const int u = u00 + ut_mine * TM + quarter * 32 + lane;
+    const float NEG = -RealTraits<float>::huge();
+    const float tau = (MODE == MODE_EMIT && u < U) ? out.tau[u] : 0.f;
+    uint4 ex_next = make_uint4(0u, 0u, 0u, 0u);
+    if (out.excl_bits && u < U && nt > 0)
+        ex_next = __ldg(reinterpret_cast<const uint4*>(out.excl_bits + (size_t)u * out.excl_words + ((t0 * TN) >> 5)));
+        for (int j = 0; j < nt; j++) {
+            pipe_wait(&mma_done[j & 1], (uint32_t)((j >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const size_t j0 = (t0 + j) * TN;
+            const uint4 ex = ex_next;                        // this user's exclusion bits of the tile's 128 items
+            if (out.excl_bits && u < U && j + 1 < nt)        // (the next tile's are fetched a tile ahead)
+                ex_next = __ldg(reinterpret_cast<const uint4*>(out.excl_bits + (size_t)u * out.excl_words + ((j0 + TN) >> 5)));
+            float gm[8];                                     // MODE_GROUPMAX: the 8 group maxima of the 128 columns
+            const uint32_t tcol = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((j & 1) * PIPE_UT + ut_mine) * TN);
+            uint32_t ra[32], rb[32];
+            tmem_ld32_async(tcol, ra);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t (&r)[32] = (c & 1) ? rb : ra;
+                tmem_ld_wait(r);
+                if (c < 3) tmem_ld32_async(tcol + (uint32_t)((c + 1) * 32), (c & 1) ? ra : rb);
+                else {      // the tile is in registers: its TMEM buffer may take tile j + 2
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_free[j & 1])) : "memory");
+                }
+                const size_t jc = j0 + c * 32;
+                uint32_t valid = ~(c == 0 ? ex.x : (c == 1 ? ex.y : (c == 2 ? ex.z : ex.w)));
+                if (jc + 32 > n) valid &= (jc >= n) ? 0u : ((1u << (unsigned)(n - jc)) - 1u);
+                if (MODE == MODE_GROUPMAX) {
+#pragma unroll
+                    for (int g = 0; g < 32 / GROUP; g++) {
+                        float m = NEG;
+                        if (((valid >> (g * GROUP)) & 0xffffu) == 0xffffu) {      // nothing masked: plain maximum
+#pragma unroll
+                            for (int q = 0; q < GROUP; q++) m = fmaxf(m, __uint_as_float(r[g * GROUP + q]));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < GROUP; q++)
+                                if ((valid >> (g * GROUP + q)) & 1u) m = fmaxf(m, __uint_as_float(r[g * GROUP + q]));
+                        }
+                        gm[c * 2 + g] = m;
+                    }
+                } else if (u < U) {
+                    float mx = NEG;                         // most 32-column blocks hold no candidate at all
+#pragma unroll
+                    for (int q = 0; q < 32; q++) mx = fmaxf(mx, __uint_as_float(r[q]));
+                    if (mx >= tau) {
+                        // rare path, kept compact (an unrolled predicated emission is ~25 KB of code and stalls the
+                        // instruction fetch): a bit per candidate column, then a loop over the set bits that picks
+                        // the value out of the registers with a 5-level select tree
+                        uint32_t hit = 0;
+#pragma unroll
+                        for (int q = 0; q < 32; q++) hit |= (__uint_as_float(r[q]) >= tau ? 1u : 0u) << q;
+                        hit &= valid;
+                        while (hit) {
+                            const int q = __ffs((int)hit) - 1;
+                            hit &= hit - 1;
+                            uint32_t t[16];
+#pragma unroll
+                            for (int e = 0; e < 16; e++) t[e] = (q & 1) ? r[2 * e + 1] : r[2 * e];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) t[e] = (q & 2) ? t[2 * e + 1] : t[2 * e];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) t[e] = (q & 4) ? t[2 * e + 1] : t[2 * e];
+#pragma unroll
+                            for (int e = 0; e < 2; e++) t[e] = (q & 8) ? t[2 * e + 1] : t[2 * e];
+                            const uint32_t vb = (q & 16) ? t[1] : t[0];
+                            const int pos = atomicAdd(out.cand_cnt + u, 1);
+                            if (pos < CAND_CAP) {
+                                out.cand_sc[(size_t)u * CAND_CAP + pos] = __uint_as_float(vb);
+                                out.cand_id[(size_t)u * CAND_CAP + pos] = (int)(jc + q);
+                            }
+                        }
+                    }
+                }
+            }
+            if (MODE == MODE_GROUPMAX && u < U) {           // 8 consecutive group maxima: two 16-byte stores when they fit
+                const size_t gi = j0 / GROUP;
+                float* dst = out.gmax + (size_t)u * out.ngroups + gi;
+                if (gi + 8 <= out.ngroups && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    reinterpret_cast<float4*>(dst)[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
+                    reinterpret_cast<float4*>(dst)[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+                } else
+                    for (int g = 0; g < 8; g++) if (gi + g < out.ngroups) dst[g] = gm[g];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * PIPE_UT * TN)) : "memory");
+}
+
+// a factor matrix [rows x ldf floats] as a 2-D tensor for the TMA unit, fetched in boxes of 32 floats x 128 rows
+// with the 128-byte swizzle
+inline int make_operand_map(CUtensorMap* map, const float* base, size_t rows, int ldf)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return 1;
+        fn = (EncodeFn)f;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)ldf, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ldf * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)PIPE_BOXK, (cuuint32_t)TM};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
 }
 
 // Exact re-scoring + final ordering of the per-user candidates.  One CTA (128 threads) per user.
