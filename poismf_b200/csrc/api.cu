@@ -29,6 +29,7 @@
 #include "devpool.h"
 #include "ingest.cuh"
 #include "staged_copy.h"
+#include <chrono>
 #include "kernels.cuh"
 #include "dense_rows.cuh"
 #include "launch.h"
@@ -1750,12 +1751,14 @@ static int upload_rows(real** dev_out, const real* host, size_t rows, int k, int
     }
     real* dev = nullptr;
     CK(dmalloc(&dev, std::max<size_t>(rows, 1) * (size_t)ldf * sizeof(real)));
+    // (pageable callers' arrays go through the multi-threaded page-locked staging of staged_copy.h)
     if (ldf == k) {
-        CK(cudaMemcpy(dev, host, rows * (size_t)k * sizeof(real), cudaMemcpyHostToDevice));
+        CK(Stager::get().h2d(dev, host, rows * (size_t)k * sizeof(real), 0));
+        CK(cudaStreamSynchronize(0));
     } else {
         real* tmp = nullptr;
         CK(dmalloc(&tmp, std::max<size_t>(rows * (size_t)k, 1) * sizeof(real)));
-        cudaError_t e = cudaMemcpy(tmp, host, rows * (size_t)k * sizeof(real), cudaMemcpyHostToDevice);
+        cudaError_t e = Stager::get().h2d(tmp, host, rows * (size_t)k * sizeof(real), 0);
         if (e == cudaSuccess) {
             pad_rows_kernel<real><<<148 * 8, 256>>>(tmp, dev, rows, k, ldf);
             LAUNCHED();
@@ -1841,6 +1844,16 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
 {
     CK(cudaSetDevice(env_device()));
     if (n_top == 0 || n_top > n) return 2;
+    // POISMF_B200_TOPN_TRACE=1: wall-clock of the call's phases on stderr (each mark synchronises the device)
+    const bool trace = getenv("POISMF_B200_TOPN_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[topN] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     // argument checks in the spirit of src/topN.c:121-128, per user: ids inside the matrices, offsets monotone,
     // enough items left after the exclusions
     if (user_ix && !A_is_single_vector)
@@ -1851,10 +1864,24 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             if (excl_ptr[u + 1] < excl_ptr[u]) return 2;
             if ((size_t)(excl_ptr[u + 1] - excl_ptr[u]) > n - n_top) return 2;
         }
-        const size_t tot = (size_t)excl_ptr[n_users];
-        for (size_t t = (size_t)excl_ptr[0]; t < tot; t++)
-            if ((size_t)excl_ix[t] >= n) return 2;
+        // (the ids themselves are range-checked on the device once uploaded: `excl_ids_ok` below)
     }
+    // -> 0 ok, 2 an excluded id outside [0, n), 1 CUDA error.  Runs before any result is written.
+    auto excl_ids_ok = [&](const IX* dev_ids, size_t count) -> int {
+        if (!count) return 0;
+        int* d_bad = nullptr;
+        int bad = 0;
+        CK(dmalloc(&d_bad, sizeof(int)));
+        cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int));
+        if (e == cudaSuccess) {
+            tc::any_id_out_of_range_kernel<IX><<<592, 256>>>(dev_ids, count, n, d_bad);
+            LAUNCHED();
+            e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        dfree(d_bad);
+        if (e != cudaSuccess) return fail("topN: id check failed: %s", cudaGetErrorString(e));
+        return bad ? 2 : 0;
+    };
     const int V = RealTraits<real>::V, ldf = round_up(k, V);
     const size_t w = (size_t)k * sizeof(real), pitch = (size_t)ldf * sizeof(real);
     // users per chunk: bound the score matrix to ~1 GiB
@@ -1878,8 +1905,11 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
     auto body = [&]() -> int {
         const size_t rowsA = A_is_single_vector ? 1 : dimA;
         bool dummy = false;
+        mark("argument checks");
         if (upload_rows<real>(&dB, B, n, k, ldf, &B_resident, true)) return 1;
+        mark("upload B");
         if (upload_rows<real>(&dA, A, rowsA, k, ldf, &dummy, false)) return 1;
+        mark("upload A");
         if (use_tc) {
             CK(dmalloc(&d_neg, sizeof(int)));
             CK(cudaMemset(d_neg, 0, sizeof(int)));
@@ -1903,7 +1933,11 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             const bool have_excl = excl_ptr && excl_ix;
             const size_t per_user = ngroups * 4 + (have_excl ? words * 4 : 0) + (size_t)tc::CAND_CAP * 8 +
                                     (size_t)tc::CAND_TOP * 8 + pitch + n_top * 12 + 64;
-            size_t fchunk = std::max<size_t>(1, std::min<size_t>(n_users, ((size_t)1 << 30) / per_user));
+            // users per batch: a quarter of the free device memory, at most 32 GB, for the per-user work arrays
+            size_t mem_free = 0, mem_total = 0;
+            CK(cudaMemGetInfo(&mem_free, &mem_total));
+            const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>(mem_free / 4, (size_t)32 << 30));
+            size_t fchunk = std::max<size_t>(1, std::min<size_t>(n_users, budget / per_user));
             fchunk = std::min<size_t>(fchunk, 32768);
             float *gmax = nullptr, *tau = nullptr, *cand_sc = nullptr, *top_sc = nullptr;
             int *cand_id = nullptr, *cand_cnt = nullptr, *top_id = nullptr, *d_ovf = nullptr;
@@ -1930,8 +1964,10 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                     CK(dmalloc(&dexp, (n_users + 1) * sizeof(IX)));
                     CK(dmalloc(&dexi, std::max<size_t>(n_excl_total, 1) * sizeof(IX)));
                     CK(cudaMemcpy(dexp, excl_ptr, (n_users + 1) * sizeof(IX), cudaMemcpyHostToDevice));
-                    CK(cudaMemcpy(dexi, excl_ix, n_excl_total * sizeof(IX), cudaMemcpyHostToDevice));
+                    CK(Stager::get().h2d(dexi, excl_ix, n_excl_total * sizeof(IX), 0));
+                    if (const int bad = excl_ids_ok(dexi + (size_t)excl_ptr[0], n_excl_total - (size_t)excl_ptr[0])) return bad;
                 }
+                mark("work arrays + exclusions up");
                 CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel<tc::MODE_GROUPMAX>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kpad * 1024));
                 CK(cudaFuncSetAttribute(tc::score_tiles_tf32_kernel<tc::MODE_EMIT>,
@@ -1963,8 +1999,18 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                                        tc::make_operand_map(&mapA, (const float*)dAsel, m, ldf) == 0 &&
                                        tc::make_operand_map(&mapB, (const float*)dB, n, ldf) == 0;
                     const unsigned ut = (unsigned)((m + tc::PIPE_UT * tc::TM - 1) / (tc::PIPE_UT * tc::TM));   // CTAs along the users
-                    // one CTA per SM (shared memory): at most one wave of CTAs, each walking a long run of item tiles
-                    const unsigned chunks = (unsigned)std::max<size_t>(1, std::min<size_t>((ntiles + 7) / 8, (size_t)num_sms / ut));
+                    // one CTA per SM (shared memory), every CTA the same run of item tiles: the split of the items
+                    // that fills whole waves best (fewest chunks among the best: the A tiles load once per CTA)
+                    unsigned chunks = 1;
+                    {
+                        double best = 0;
+                        const unsigned cmax = (unsigned)std::max<size_t>(1, std::min<size_t>(ntiles / 32, 64));
+                        for (unsigned c = 1; c <= cmax; c++) {
+                            const size_t ctas = (size_t)c * ut, waves = (ctas + num_sms - 1) / num_sms;
+                            const double eff = (double)ctas / (double)(waves * num_sms);
+                            if (eff > best + 0.02) { best = eff; chunks = c; }
+                        }
+                    }
                     const int tiles_per_cta = (int)((ntiles + chunks - 1) / chunks);
                     const size_t pipe_smem = (size_t)(tc::PIPE_UT + tc::PIPE_STAGES) * ((kpad + tc::PIPE_BOXK - 1) / tc::PIPE_BOXK) * 16384;
                     if (piped) {
@@ -1995,21 +2041,38 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                                                                     4e-3f, d_out_ids, d_out_sc, d_flag);
                     LAUNCHED();
                     CK(cudaGetLastError());
-                    hid.resize(m * n_top); hsc.resize(m * n_top); hfl.resize(m); hov.resize(m);
-                    CK(cudaMemcpy(hid.data(), d_out_ids, m * n_top * sizeof(long long), cudaMemcpyDeviceToHost));
-                    CK(cudaMemcpy(hsc.data(), d_out_sc, m * n_top * sizeof(float), cudaMemcpyDeviceToHost));
+                    mark("batch kernels");
+                    // results straight into the caller's arrays when the element types agree (they do for the
+                    // reference's size_t / float build); staged through page-locked blocks when those are pageable
+                    hfl.resize(m); hov.resize(m);
+                    if (sizeof(IX) == sizeof(long long)) {
+                        CK(Stager::get().d2h((void*)(outp_ix + u0 * n_top), d_out_ids, m * n_top * sizeof(long long), 0));
+                    } else {
+                        hid.resize(m * n_top);
+                        CK(cudaMemcpy(hid.data(), d_out_ids, m * n_top * sizeof(long long), cudaMemcpyDeviceToHost));
+                        for (size_t i = 0; i < m * n_top; i++) outp_ix[u0 * n_top + i] = (IX)hid[i];
+                    }
+                    if (outp_score) {
+                        if (std::is_same<real, float>::value) {
+                            CK(Stager::get().d2h((void*)(outp_score + u0 * n_top), d_out_sc, m * n_top * sizeof(float), 0));
+                        } else {
+                            hsc.resize(m * n_top);
+                            CK(cudaMemcpy(hsc.data(), d_out_sc, m * n_top * sizeof(float), cudaMemcpyDeviceToHost));
+                            for (size_t i = 0; i < m * n_top; i++) outp_score[u0 * n_top + i] = (real)hsc[i];
+                        }
+                    }
                     CK(cudaMemcpy(hfl.data(), d_flag, m * sizeof(int), cudaMemcpyDeviceToHost));
                     CK(cudaMemcpy(hov.data(), d_ovf, m * sizeof(int), cudaMemcpyDeviceToHost));
-                    for (size_t i = 0; i < m * n_top; i++) outp_ix[u0 * n_top + i] = (IX)hid[i];
-                    if (outp_score) for (size_t i = 0; i < m * n_top; i++) outp_score[u0 * n_top + i] = (real)hsc[i];
                     for (size_t u = 0; u < m; u++) if (hfl[u] || hov[u]) redo.push_back(u0 + u);
                     g_topn_stats[0] += m;
+                    mark("batch results down");
                 }
                 return 0;
             };
             const int frc = fused();
             if (frc) cudaDeviceSynchronize();
             for (void* q : mine) dfree(q);
+            mark("release");
             return frc;
         }
         if (use_tc) {
@@ -2034,7 +2097,8 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             CK(dmalloc(&dexp, (n_users + 1) * sizeof(IX)));
             CK(dmalloc(&dexi, std::max<size_t>(n_excl_total, 1) * sizeof(IX)));
             CK(cudaMemcpy(dexp, excl_ptr, (n_users + 1) * sizeof(IX), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(dexi, excl_ix, n_excl_total * sizeof(IX), cudaMemcpyHostToDevice));
+            CK(Stager::get().h2d(dexi, excl_ix, n_excl_total * sizeof(IX), 0));
+            if (const int bad = excl_ids_ok(dexi + (size_t)excl_ptr[0], n_excl_total - (size_t)excl_ptr[0])) return bad;
         }
         size_t tmp_bytes = 0;
         CK(cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tmp_bytes, sc_in, sc_out, id_in, id_out,

@@ -587,29 +587,75 @@ __global__ void exclusion_bitmap_kernel(uint32_t* __restrict__ bits, size_t word
     }
 }
 
-// tau[u] = the M-th largest of the user's group maxima (most-significant-digit radix select on the
-// order-preserving keys, 8 bits a round).  One CTA of 256 threads per user.
+// tau[u] = the M-th largest of the user's group maxima, in two reads of the row (it is HBM traffic that this
+// kernel costs: 250 KB per user at 1M items).  Read 1: a 4096-bin histogram of the top 12 key bits (exponent + 4
+// mantissa bits); a block-wide suffix sum finds the bin that holds the M-th largest.  Read 2: that bin's keys
+// (a few hundred) are collected in shared memory and a radix select on their low 19 bits finishes there.
+// A bin with more keys than the list holds falls back to the bin's lower edge — a smaller threshold, i.e. more
+// candidates, never fewer.  One CTA of 256 threads per user.
+constexpr int SEL_BINS = 4096, SEL_LIST = 4096, SEL_SHIFT = 19;
 __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __restrict__ gmax, size_t ngroups, int M,
                                                                float* __restrict__ tau)
 {
-    __shared__ unsigned int hist[256];
+    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ unsigned int part[256];
+    __shared__ uint32_t list[SEL_LIST];
     __shared__ uint32_t s_prefix;
-    __shared__ int s_want;
+    __shared__ int s_want, s_cnt;
     const float* g = gmax + (size_t)blockIdx.x * ngroups;
     const int tid = threadIdx.x;
-    if (tid == 0) { s_prefix = 0u; s_want = M; }
-    uint32_t mask = 0u;
-    for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < SEL_BINS; i += 256) hist[i] = 0u;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (size_t i = tid; i < ngroups; i += 256) atomicAdd(&hist[score_key(g[i]) >> SEL_SHIFT], 1u);
+    __syncthreads();
+    unsigned int mine = 0;                                  // thread t owns bins [16 t, 16 t + 16)
+    for (int b = 0; b < 16; b++) mine += hist[16 * tid + b];
+    part[tid] = mine;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {               // part[t] = keys in the bins of threads >= t
+        const unsigned int v = tid + off < 256 ? part[tid + off] : 0u;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    const unsigned int above = part[tid] - mine;
+    if (above < (unsigned)M && (unsigned)M <= above + mine) {      // the M-th largest lies in my bins
+        int want = M - (int)above, b = 15;
+        for (; b > 0; b--) {
+            const int c = (int)hist[16 * tid + b];
+            if (c >= want) break;
+            want -= c;
+        }
+        s_prefix = (uint32_t)(16 * tid + b) << SEL_SHIFT;
+        s_want = want;
+    }
+    __syncthreads();
+    uint32_t prefix = s_prefix;
+    const unsigned int in_bin = hist[prefix >> SEL_SHIFT];
+    if (in_bin > (unsigned)SEL_LIST) {
+        if (tid == 0) tau[blockIdx.x] = key_score(prefix);
+        return;
+    }
+    for (size_t i = tid; i < ngroups; i += 256) {
+        const uint32_t key = score_key(g[i]);
+        if ((key >> SEL_SHIFT) == (prefix >> SEL_SHIFT)) list[atomicAdd(&s_cnt, 1)] = key;
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    uint32_t mask = ~0u << SEL_SHIFT;
+    for (int round = 0; round < 3; round++) {               // low 19 bits: digits of 8, 8 and 3 bits
+        const int shift = round == 0 ? 11 : (round == 1 ? 3 : 0);
+        const uint32_t dmask = round == 2 ? 7u : 255u;
         hist[tid] = 0u;
         __syncthreads();
-        const uint32_t prefix = s_prefix;
-        for (size_t i = tid; i < ngroups; i += 256) {
-            const uint32_t key = score_key(g[i]);
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        for (int i = tid; i < cnt; i += 256) {
+            const uint32_t key = list[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
         }
         __syncthreads();
         if (tid == 0) {     // walk the digits from the top until `want` keys have been passed
-            int want = s_want, d = 255;
+            int want = s_want, d = (int)dmask;
             for (; d > 0; d--) {
                 const int c = (int)hist[d];
                 if (c >= want) break;
@@ -618,10 +664,12 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
             s_prefix = prefix | ((uint32_t)d << shift);
             s_want = want;
         }
-        mask |= 255u << shift;
+        __syncthreads();
+        prefix = s_prefix;
+        mask |= dmask << shift;
         __syncthreads();
     }
-    if (tid == 0) tau[blockIdx.x] = key_score(s_prefix);
+    if (tid == 0) tau[blockIdx.x] = key_score(prefix);
 }
 
 // Order one user's candidates by (score desc, id asc) and keep the best CAND_TOP (padded with -huge).
@@ -669,6 +717,17 @@ __global__ void any_negative_kernel(const float* __restrict__ x, size_t n, int* 
     int f = 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         f |= (x[i] < 0.f);
+    if (f) atomicOr(flag, 1);
+}
+
+// flag |= 1 when an id lies outside [0, n)  (the batched entry's check of the exclusion lists: millions of ids
+// that are on the device anyway; a negative id of a signed type is a huge size_t)
+template <class IX>
+__global__ void any_id_out_of_range_kernel(const IX* __restrict__ ids, size_t count, size_t n, int* __restrict__ flag)
+{
+    int f = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        f |= ((size_t)ids[i] >= n);
     if (f) atomicOr(flag, 1);
 }
 
