@@ -502,26 +502,49 @@ def main():
         ts = []
         h2d = d2h = 0
         outA, outB = np.empty_like(A0), np.empty_like(B0)
+        pin = []             # page-locked host buffers, as in the N=1 leg (slices of them are page-locked too)
+        for arr in (csr[0], csr[1], csr[2], csc[0], csc[1], csc[2], A0, B0, outA, outB):
+            tt = torch.from_numpy(arr)
+            try:
+                torch.cuda.cudart().cudaHostRegister(tt.data_ptr(), tt.numel() * tt.element_size(), 0)
+                pin.append(tt)
+            except Exception:
+                pass
+        trace = bool(os.environ.get("POISMF_B200_BENCH_TRACE"))      # (every rank: finish() holds a barrier)
         for it in range(4):
             dist.barrier()
             t0 = time.perf_counter()
             be.load(csr, csc, A0, B0)
+            t1 = time.perf_counter()
             ShardedSweep(be, dimA, dimB, np.float32).run(params)
+            if trace:
+                be.finish()
+            t2 = time.perf_counter()
             be.factors(root=0, out=(outA, outB))
+            t3 = time.perf_counter()
             dist.barrier()
             dt = time.perf_counter() - t0
+            if trace and rank == 0:
+                print(f"[e2e N={world}] load {1e3 * (t1 - t0):.2f} ms, sweep {1e3 * (t2 - t1):.2f} ms, factors "
+                      f"{1e3 * (t3 - t2):.2f} ms, total {1e3 * dt:.2f} ms", file=sys.stderr)
             a0, a1 = be.rangesA[rank]; b0, b1 = be.rangesB[rank]
             h2d = ((A0.nbytes + B0.nbytes) // world + int(csr[1][a1] - csr[1][a0]) * 12 + int(csc[1][b1] - csc[1][b0]) * 12
                    + (a1 - a0 + b1 - b0) * 8)
             d2h = A0.nbytes + B0.nbytes if rank == 0 else 0
             if it > 0:
                 ts.append(dt)
+        for tt in pin:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(tt.data_ptr())
+            except Exception:
+                pass
         t = torch.tensor([float(np.mean(ts))], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = 1e3 * float(t.item())
         e2e = {"value": nnz / (e_ms / 1e3), "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e_ms, "steps": len(ts),
-               "call": "GpuBackend.load + ShardedSweep.run(numiter=1) + factors(root=0) on a persistent backend: every rank "
+               "call": "GpuBackend.load + ShardedSweep.run(numiter=1) + factors(root=0) on a persistent backend, host buffers "
+                       "cudaHostRegister'ed: every rank "
                        "uploads its matrix shard and 1/N of the initial factors (stored into all replicas over NVLink), plan, "
                        "sweep with the fused exchange, rank 0 reads A and B back (max over ranks; bytes are per rank)"}
 

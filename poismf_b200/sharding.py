@@ -25,9 +25,12 @@ def row_cost(nnz_per_row):
     """Relative device cost of solving a row with n non-zeros (measured on B200, r1 bins of config #2):
     ~10 non-zero-equivalents of fixed work per row, and non-zeros of long rows cost more — rows beyond
     one CTA's shared memory pay cluster barriers (x2), rows streamed from L2 more again (x3)."""
-    n = np.asarray(nnz_per_row, dtype=np.float64)
-    f = np.where(n <= 1000, 1.0, np.where(n <= 16000, 2.0, 3.0))
-    return np.where(n > 0, 10.0 + n * f, 0.0)
+    n = np.asarray(nnz_per_row).astype(np.float64)
+    c = n + 10.0                        # (in-place arithmetic: this runs inside every sharded load)
+    c += n * (n > 1000)
+    c += n * (n > 16000)
+    c[n <= 0] = 0.0
+    return c
 
 
 def nnz_balanced_ranges(indptr, nparts, cost_aware=True):
@@ -39,7 +42,8 @@ def nnz_balanced_ranges(indptr, nparts, cost_aware=True):
     indptr = np.asarray(indptr).astype(np.int64)
     n = indptr.shape[0] - 1
     if cost_aware:
-        cum = np.concatenate([[0.0], np.cumsum(row_cost(np.diff(indptr)))])
+        cum = np.zeros(n + 1)
+        np.cumsum(row_cost(np.diff(indptr)), out=cum[1:])
     else:
         cum = (indptr - indptr[0]).astype(np.float64)
     total = float(cum[-1])
@@ -154,8 +158,8 @@ class GpuBackend:
         from . import _lib
         self.finish()
         world, rank = self.world, self.rank
-        self.rangesA = nnz_balanced_ranges(csr[1], world)
-        self.rangesB = nnz_balanced_ranges(csc[1], world)
+        self.rangesA = self._ranges(csr[1])
+        self.rangesB = self._ranges(csc[1])
         a0, a1 = self.rangesA[rank]
         b0, b1 = self.rangesB[rank]
         lr = slice_compressed(csr, a0, a1)
@@ -164,6 +168,20 @@ class GpuBackend:
         self.fit.set_matrix(_lib.SIDE_CSR, *lr, row_begin=a0, n_rows=a1 - a0)
         self.fit.set_matrix(_lib.SIDE_CSC, *lc, row_begin=b0, n_rows=b1 - b0)
         self._set_factors(A0, B0)
+
+    def _ranges(self, indptr):
+        """Shard boundaries of one side, remembered per offsets array (address, length, a strided sample of
+        its content) — a refit on the same matrix skips the cost model's passes over every row."""
+        indptr = np.asarray(indptr)
+        step = max(1, indptr.shape[0] // 1024)
+        key = (indptr.__array_interface__["data"][0], indptr.shape[0], indptr.dtype.str, self.world,
+               indptr[::step].tobytes(), int(indptr[-1]))
+        cache = self.__dict__.setdefault("_ranges_cache", {})
+        if key not in cache:
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = nnz_balanced_ranges(indptr, self.world)
+        return cache[key]
 
     def _set_factors(self, A0, B0):
         if self.mode == "nccl":
