@@ -2012,14 +2012,15 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                         }
                     }
                     const int tiles_per_cta = (int)((ntiles + chunks - 1) / chunks);
-                    const size_t pipe_smem = (size_t)(tc::PIPE_UT + tc::PIPE_STAGES) * ((kpad + tc::PIPE_BOXK - 1) / tc::PIPE_BOXK) * 16384;
+                    const size_t pipe_smem = tc::pipe_smem_bytes(kpad);
+                    const int pipe_stages = tc::pipe_stages(kpad);
                     if (piped) {
                         CK(cudaFuncSetAttribute(tc::score_pipe_tf32_kernel<tc::MODE_GROUPMAX>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
                         CK(cudaFuncSetAttribute(tc::score_pipe_tf32_kernel<tc::MODE_EMIT>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
                         tc::score_pipe_tf32_kernel<tc::MODE_GROUPMAX><<<dim3(chunks, ut), tc::PIPE_THREADS, pipe_smem>>>(
-                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, o);
+                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, pipe_stages, o);
                     } else
                         tc::score_tiles_tf32_kernel<tc::MODE_GROUPMAX><<<tgrid, 128, (size_t)kpad * 1024>>>(
                             (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
@@ -2029,7 +2030,7 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                     CK(cudaMemsetAsync(cand_cnt, 0, m * sizeof(int)));
                     if (piped)
                         tc::score_pipe_tf32_kernel<tc::MODE_EMIT><<<dim3(chunks, ut), tc::PIPE_THREADS, pipe_smem>>>(
-                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, o);
+                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, pipe_stages, o);
                     else
                         tc::score_tiles_tf32_kernel<tc::MODE_EMIT><<<tgrid, 128, (size_t)kpad * 1024>>>(
                             (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) score_tiles_tf32_kernel(const float* __re
 //                         -> tcgen05.commit to stage_free[s] and to mma_done[b]
 //     warps 0..7        : wait mma_done[b] -> TMEM -> registers (arrive on tmem_free[b] as soon as the last load
 //                         has landed) -> group maxima / candidates
-constexpr int PIPE_STAGES = 3;
+constexpr int PIPE_STAGES = 3;       // at most; fewer when k is large (pipe_stages() below)
 constexpr int PIPE_UT = 2;           // user tiles per CTA
 constexpr int PIPE_BOXK = 32;        // floats per TMA box along k (128 bytes: the swizzle span)
 constexpr int PIPE_THREADS = 320;    // 8 epilogue warps, the MMA warp, the TMA warp
@@ -318,14 +318,16 @@ PMF_DEVINL uint64_t make_smem_desc_sw128(uint32_t saddr)
 }
 
 // grid = (item-tile chunks, pairs of user tiles), PIPE_THREADS threads, dynamic shared memory
-// (PIPE_UT + PIPE_STAGES) * nbox * 16 KB with nbox = ceil(kpad / 32).
+// pipe_smem_bytes(kpad) = (PIPE_UT + stages) * nbox * 16 KB + 1 KB with nbox = ceil(kpad / 32).
 // Epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (its quarter; = tile rows = users) of user tile w / 4.
 template <int MODE>
 __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB, int U, size_t n,
-                                                              int kpad, int tiles_per_cta, TileOut out)
+                                                              int kpad, int tiles_per_cta, int nstages, TileOut out)
 {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // the 128-byte swizzle works on 1024-byte atoms: align the operand area whatever the static variables take
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full[PIPE_STAGES], stage_free[PIPE_STAGES], mma_done[2], tmem_free[2], a_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -364,8 +366,8 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
                 for (int bx = 0; bx < nbox; bx++)
                     tma_box(sA + (size_t)ut * tile_bytes + (size_t)bx * box_bytes, &mapA, bx * PIPE_BOXK, u00 + ut * TM, &a_full);
             for (int i = 0; i < nt; i++) {
-                const int s = i % PIPE_STAGES;
-                if (i >= PIPE_STAGES) pipe_wait(&stage_free[s], (uint32_t)((i / PIPE_STAGES - 1) & 1));
+                const int s = i % nstages;
+                if (i >= nstages) pipe_wait(&stage_free[s], (uint32_t)((i / nstages - 1) & 1));
                 pipe_expect(&full[s], tile_bytes);
                 for (int bx = 0; bx < nbox; bx++)
                     tma_box(sB + (size_t)s * tile_bytes + (size_t)bx * box_bytes, &mapB, bx * PIPE_BOXK, (int)((t0 + i) * TN), &full[s]);
@@ -376,8 +378,8 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
             const uint32_t a0 = smem_u32(sA), b00 = smem_u32(sB);
             pipe_wait(&a_full, 0);
             for (int i = 0; i < nt; i++) {
-                const int s = i % PIPE_STAGES, b = i & 1;
-                pipe_wait(&full[s], (uint32_t)((i / PIPE_STAGES) & 1));
+                const int s = i % nstages, b = i & 1;
+                pipe_wait(&full[s], (uint32_t)((i / nstages) & 1));
                 if (i >= 2) pipe_wait(&tmem_free[b], (uint32_t)(((i >> 1) - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t db0 = make_smem_desc_sw128(b00 + (uint32_t)s * tile_bytes);
@@ -488,6 +490,20 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * PIPE_UT * TN)) : "memory");
+}
+
+// operand stages that fit next to the two user tiles (227 KB per CTA; k <= 64: 3, k <= 96: 2, k <= 128: 1) and
+// the dynamic shared memory of the launch (+1 KB for the alignment)
+inline int pipe_stages(int kpad)
+{
+    const size_t tile = (size_t)((kpad + PIPE_BOXK - 1) / PIPE_BOXK) * TM * PIPE_BOXK * 4;
+    const size_t room = (size_t)226 * 1024 - 1024 - PIPE_UT * tile;
+    return (int)std::max<size_t>(1, std::min<size_t>(PIPE_STAGES, room / tile));
+}
+inline size_t pipe_smem_bytes(int kpad)
+{
+    const size_t tile = (size_t)((kpad + PIPE_BOXK - 1) / PIPE_BOXK) * TM * PIPE_BOXK * 4;
+    return (size_t)(PIPE_UT + pipe_stages(kpad)) * tile + 1024;
 }
 
 // a factor matrix [rows x ldf floats] as a 2-D tensor for the TMA unit, fetched in boxes of 32 floats x 128 rows

@@ -613,7 +613,7 @@ def test_factors_single_matches_oracle(dtype, case):
 
 
 # ---------------------------------------------------------------- batched topN on the tensor cores
-@pytest.mark.parametrize("k,n_top", [(64, 100), (50, 10), (7, 37)])
+@pytest.mark.parametrize("k,n_top", [(64, 100), (50, 10), (7, 37), (96, 20), (128, 10)])
 def test_topn_batch_tensor_core_path_is_exact(k, n_top):
     """The tcgen05/TF32 scorer only proposes candidates; rankings must equal the exact FP32 ones
     (ids identical wherever the exact scores are not tied) and most users must NOT need the exact
@@ -675,6 +675,27 @@ def test_topn_fused_select_edge_cases(monkeypatch):
     ix3, sc3 = c_funs._topN_batch(A[:8], Bt, top_n=n_top, output_score=True)
     assert _lib.topn_stats(reset=True)[1] == 8
     assert all(len(set(r.tolist())) == n_top for r in ix3) and (sc3 == sc3[:, :1]).all()
+
+
+def test_topn_threshold_select_crowded_bin(monkeypatch):
+    """More group maxima in the threshold's histogram bin than the select's shared-memory list holds (70k items
+    whose scores lie within 0.1 % of each other): the threshold falls back to the bin's lower edge, every item
+    becomes a candidate, the candidate lists overflow and the users are redone exactly — same result as the
+    exact scorer."""
+    from poismf_b200 import _lib, c_funs
+    rng = np.random.default_rng(5)
+    k, n_items, n_users, n_top = 32, 70_000, 40, 25
+    A = np.ascontiguousarray(rng.gamma(2.0, 0.5, size=(n_users, k)).astype(np.float32))
+    base = rng.gamma(2.0, 0.5, size=(1, k))
+    B = np.ascontiguousarray((base * (1.0 + 1e-3 * rng.random((n_items, 1)))).astype(np.float32))
+    _lib.topn_stats(reset=True)
+    ix, sc = c_funs._topN_batch(A, B, top_n=n_top, output_score=True)
+    n_tc, n_redo = _lib.topn_stats(reset=True)
+    assert n_tc == n_users and n_redo == n_users
+    monkeypatch.setenv("POISMF_B200_TOPN_EXACT", "1")
+    ix2, sc2 = c_funs._topN_batch(A, B, top_n=n_top, output_score=True)
+    assert np.array_equal(sc, sc2)
+    assert all((sc[u] == sc[u][t]).sum() > 1 for u, t in zip(*np.nonzero(ix != ix2)))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
