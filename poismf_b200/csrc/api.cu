@@ -948,7 +948,8 @@ template <class real> struct HandleT : pmf_b200_handle {
                     const int v = e ? atoi(e) : NAUX;
                     return v < 1 ? 1 : (v > NAUX ? NAUX : v);
                 }();
-                const int si = n_launched % n_streams;
+                // (the lock-step chain keeps aux[0] to itself: a bin queued behind it would start when it ends)
+                const int si = (S.dense.H > 0 && n_streams > 1) ? 1 + (n_launched - 1) % (n_streams - 1) : n_launched % n_streams;
                 ls = aux[si];
                 if (!used[si]) { CK(cudaStreamWaitEvent(ls, ev_fork, 0)); used[si] = true; }
             }
