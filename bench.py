@@ -211,10 +211,25 @@ def bench_topn(args, rank, world, local_rank):
     ts = [one() for _ in range(args.steps)]
     n_tc, n_redo = _lib.topn_stats(reset=True)
     ms = 1e3 * float(np.mean(ts))
+    # the same ranking against factors RESIDENT in a fit handle (pmf_b200_topN_fitted: what follows a fit on the
+    # device; every rank of a sharded fit holds full replicas): only ids and exclusion lists travel
+    from poismf_b200.device import DeviceFit
+    fit = DeviceFit(t["users"], t["items"], t["k"], np.float32, device=local_rank)
+    fit.set_factors(A, B)
+
+    def one_resident():
+        t0 = time.perf_counter()
+        fit.topN(users=users, excl_ptr=lptr, excl_ix=leix, top_n=t["top_n"], output_score=True)
+        return time.perf_counter() - t0
+    for _ in range(max(args.warmup, 1)):
+        one_resident()
     if dist is not None:
-        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.barrier()
+    ms_res = 1e3 * float(np.mean([one_resident() for _ in range(args.steps)]))
+    if dist is not None:
+        tt = torch.tensor([ms, ms_res], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+        ms, ms_res = float(tt[0].item()), float(tt[1].item())
     if rank == 0:
         peaks = {}
         try:
@@ -222,7 +237,7 @@ def bench_topn(args, rank, world, local_rank):
         except Exception:
             pass
         # dense tf32 peak: half the measured bf16 cuBLAS figure (B200_PROFILING.md: 1.1 vs 2.25 PF nominal)
-        peak = float(peaks.get("bf16_tflops", 1590.0)) / 2
+        peak = float(peaks.get("bf16_tflops", 1590.0)) / 2 * args.gpus          # all GPUs of the job
         flops = 2.0 * t["users"] * t["items"] * t["k"] * 2          # two scoring passes (threshold, candidates)
         line = {"metric": "users ranked/sec (batched topN)", "value": t["users"] / (ms / 1e3), "unit": "users/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -232,7 +247,11 @@ def bench_topn(args, rank, world, local_rank):
                 "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                              "frac": flops / (ms / 1e3) / 1e12 / peak, "traffic": None,
                              "note": "end-to-end call (upload of A, B and the exclusion lists, two TF32 scoring passes, exact "
-                                     "re-score, download) against half the measured bf16 cuBLAS peak"},
+                                     "re-score, download) against half the measured bf16 cuBLAS peak of the job's GPUs"},
+                "resident": {"value": t["users"] / (ms_res / 1e3), "unit": "users/s", "ms_per_step": ms_res,
+                             "tensor_frac": flops / (ms_res / 1e3) / 1e12 / peak,
+                             "call": "pmf_b200_topN_fitted: factors resident in a fit handle, ids + exclusion lists up, "
+                                     "rankings + scores down"},
                 "topn_users_on_tensor_cores": int(n_tc), "topn_users_redone_exactly": int(n_redo)}
         print(json.dumps(line))
     if dist is not None:

@@ -195,6 +195,16 @@ int pmf_b200_topN_batch(int dtype, int index_bytes, const void* A, const void* B
                         const void* excl_ptr, const void* excl_ix,
                         void* outp_ix, void* outp_score, size_t n_top, size_t n);
 
+/* The same ranking against the factors RESIDENT in a handle (after pmf_b200_sweeps / half_sweep, set_factors or
+ * set_factor_rows): A = the handle's dimA x k user factors, B = its dimB x k item factors; only the user ids and
+ * the exclusion lists are uploaded.  The call first waits for the handle's stream and, in a sharded fit, for
+ * the peers' rows of the last half-sweep (like pmf_b200_sync), so every rank of a sharded fit can rank its own
+ * share of the users against its replicas right after the last sweep (PoisMF.fit -> topN without a round trip
+ * of the factors through the host, poismf/__init__.py:440,914-923).  Same return codes as pmf_b200_topN_batch. */
+int pmf_b200_topN_fitted(pmf_b200_handle* h, int index_bytes, const void* user_ix, size_t n_users,
+                         const void* excl_ptr, const void* excl_ix,
+                         void* outp_ix, void* outp_score, size_t n_top);
+
 /* Counters of the calling thread's topN calls: users scored by the tensor-core candidate scorer,
  * and how many of those had to be redone by the exact scorer because the TF32 error bound could
  * not prove their candidate set complete. */

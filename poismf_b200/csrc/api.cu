@@ -1835,15 +1835,18 @@ extern "C" int pmf_b200_predict_multiple(int dtype, int index_bytes, void* out, 
 }
 
 // ---- topN ----------------------------------------------------------------------
+struct ResidentFactors { const void* A; const void* B; int device; int ldf; };
+
 // v1: exact scores (same sums as the reference) + CUB segmented radix sort.
 // Ranking = descending score; ties by ascending item id (the reference's tie order
 // is qsort's, i.e. unspecified).
 template <class real, class IX>
 static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_ix, size_t n_users, size_t dimA,
                            const IX* excl_ptr, const IX* excl_ix, IX* outp_ix, real* outp_score, size_t n_top, size_t n,
-                           bool A_is_single_vector, bool allow_tc = true)
+                           bool A_is_single_vector, bool allow_tc = true, const ResidentFactors* rf = nullptr)
 {
-    CK(cudaSetDevice(env_device()));
+    // rf: the factors already sit on a device, padded to ldf (a fit handle's replicas): nothing is uploaded
+    CK(cudaSetDevice(rf ? rf->device : env_device()));
     if (n_top == 0 || n_top > n) return 2;
     // POISMF_B200_TOPN_TRACE=1: wall-clock of the call's phases on stderr (each mark synchronises the device)
     const bool trace = getenv("POISMF_B200_TOPN_TRACE") != nullptr;
@@ -1902,15 +1905,22 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
     const int M_cand = (int)std::min<size_t>(n, std::min<size_t>(256, std::max<size_t>(2 * n_top, n_top + 32)));
     long long* d_out_ids = nullptr; float* d_out_sc = nullptr; int* d_flag = nullptr; int* d_neg = nullptr;
     bool B_resident = false;           // dB belongs to the resident-matrix cache: not released here
+    bool A_resident = false;           // (both belong to a fit handle)
     std::vector<size_t> redo;          // users whose TF32 proof failed: redone exactly afterwards
     auto body = [&]() -> int {
         const size_t rowsA = A_is_single_vector ? 1 : dimA;
         bool dummy = false;
         mark("argument checks");
-        if (upload_rows<real>(&dB, B, n, k, ldf, &B_resident, true)) return 1;
-        mark("upload B");
-        if (upload_rows<real>(&dA, A, rowsA, k, ldf, &dummy, false)) return 1;
-        mark("upload A");
+        if (rf) {
+            if (rf->ldf != ldf) return fail("topN: resident factors have another row pitch");
+            dB = (real*)rf->B; dA = (real*)rf->A;
+            B_resident = A_resident = true;
+        } else {
+            if (upload_rows<real>(&dB, B, n, k, ldf, &B_resident, true)) return 1;
+            mark("upload B");
+            if (upload_rows<real>(&dA, A, rowsA, k, ldf, &dummy, false)) return 1;
+            mark("upload A");
+        }
         if (use_tc) {
             CK(dmalloc(&d_neg, sizeof(int)));
             CK(cudaMemset(d_neg, 0, sizeof(int)));
@@ -2161,7 +2171,8 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
     int rc = body();
     if (rc) cudaDeviceSynchronize();
     if (!B_resident) dfree(dB);
-    dfree(dA); dfree(dAsel); dfree(sc_in); dfree(sc_out); dfree(id_in);
+    if (!A_resident) dfree(dA);
+    dfree(dAsel); dfree(sc_in); dfree(sc_out); dfree(id_in);
     dfree(id_out); dfree(seg); dfree(dusers); dfree(dexp); dfree(dexi); dfree(tmp);
     dfree(d_out_ids); dfree(d_out_sc); dfree(d_flag); dfree(d_neg);
     // users whose candidate set could not be proven complete: exact scorer, one call for all of them
@@ -2182,7 +2193,7 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
         rc = topn_batch_impl<real, IX>(A, B, k, A_is_single_vector ? nullptr : ru.data(), R, dimA,
                                        (excl_ptr && excl_ix) ? rptr.data() : nullptr,
                                        (excl_ptr && excl_ix) ? (rix.empty() ? rptr.data() : rix.data()) : nullptr,
-                                       rout.data(), outp_score ? rsc.data() : nullptr, n_top, n, A_is_single_vector, false);
+                                       rout.data(), outp_score ? rsc.data() : nullptr, n_top, n, A_is_single_vector, false, rf);
         for (size_t i = 0; i < R && !rc; i++) {
             memcpy(outp_ix + redo[i] * n_top, &rout[i * n_top], n_top * sizeof(IX));
             if (outp_score) memcpy(outp_score + redo[i] * n_top, &rsc[i * n_top], n_top * sizeof(real));
@@ -2241,6 +2252,26 @@ extern "C" void pmf_b200_topN_stats(unsigned long long* tensor_core_users, unsig
     if (tensor_core_users) *tensor_core_users = g_topn_stats[0];
     if (redone_exact) *redone_exact = g_topn_stats[1];
     if (reset) g_topn_stats[0] = g_topn_stats[1] = 0;
+}
+
+// batched topN against the factors RESIDENT in a handle (after a fit, or set_factors / set_factor_rows): nothing
+// but the user ids and the exclusion lists travels to the device.  In a sharded fit every rank holds full
+// replicas of A and B, so each rank can rank its own share of the users right after the last sweep.
+extern "C" int pmf_b200_topN_fitted(pmf_b200_handle* h, int index_bytes, const void* user_ix, size_t n_users,
+                                    const void* excl_ptr, const void* excl_ix, void* outp_ix, void* outp_score,
+                                    size_t n_top)
+{
+    if (!h) return fail("topN_fitted: null handle");
+    if (pmf_b200_sync(h)) return 1;             // every row of the last half-sweep (own and peers') has landed
+    ResidentFactors rf = {h->factor_ptr(0), h->factor_ptr(1), h->device, h->ldf};
+    if (!rf.A || !rf.B) return fail("topN_fitted: the handle holds no factors");
+    const size_t dimA = h->dimA, n = h->dimB;
+    const int k = h->k;
+    if (h->dtype == PMF_F32 && index_bytes == 8) return topn_batch_impl<float, uint64_t>(nullptr, nullptr, k, (const uint64_t*)user_ix, n_users, dimA, (const uint64_t*)excl_ptr, (const uint64_t*)excl_ix, (uint64_t*)outp_ix, (float*)outp_score, n_top, n, false, true, &rf);
+    if (h->dtype == PMF_F32 && index_bytes == 4) return topn_batch_impl<float, int>(nullptr, nullptr, k, (const int*)user_ix, n_users, dimA, (const int*)excl_ptr, (const int*)excl_ix, (int*)outp_ix, (float*)outp_score, n_top, n, false, true, &rf);
+    if (h->dtype == PMF_F64 && index_bytes == 8) return topn_batch_impl<double, uint64_t>(nullptr, nullptr, k, (const uint64_t*)user_ix, n_users, dimA, (const uint64_t*)excl_ptr, (const uint64_t*)excl_ix, (uint64_t*)outp_ix, (double*)outp_score, n_top, n, false, true, &rf);
+    if (h->dtype == PMF_F64 && index_bytes == 4) return topn_batch_impl<double, int>(nullptr, nullptr, k, (const int*)user_ix, n_users, dimA, (const int*)excl_ptr, (const int*)excl_ix, (int*)outp_ix, (double*)outp_score, n_top, n, false, true, &rf);
+    return fail("topN_fitted: bad dtype/index width");
 }
 
 extern "C" int pmf_b200_topN_batch(int dtype, int index_bytes, const void* A, const void* B, int k,

@@ -248,6 +248,18 @@ class GpuBackend:
         return self.fit.get_factors(*(out or (None, None)))
 
 
+    def topN(self, top_n, users=None, excl_ptr=None, excl_ix=None, output_score=False):
+        """Batched top-N after the fit, users split across the ranks: every rank ranks its share against ITS
+        replicas of A and B (resident: pmf_b200_topN_fitted, no factor leaves or enters a GPU) and the per-user
+        lists are all-gathered.  Every rank returns the full (n_users x top_n) result."""
+        dimA, dimB, dt = self.fit.dimA, self.fit.dimB, self.fit.dtype
+        scorer = lambda A_, B_, u_, p_, i_, n_, s_: self.fit.topN(users=u_, excl_ptr=p_, excl_ix=i_, top_n=n_,
+                                                                  output_score=s_)
+        return topn_sharded(np.empty((dimA, 0), dt), np.empty((dimB, 0), dt), top_n, users=users, excl_ptr=excl_ptr,
+                            excl_ix=excl_ix, output_score=output_score, rank=self.rank, world=self.world,
+                            group=self.group, scorer=scorer)
+
+
 def user_ranges(n_users, nparts):
     """Contiguous, near-equal user ranges (topN work per user is the same: n items x k)."""
     cuts = [n_users * p // nparts for p in range(nparts + 1)]

@@ -338,6 +338,8 @@ def _two_gpu_worker(rank, world, port, exchange, q):
         ShardedSweep(be, A0.shape[0], B0.shape[0], dtype).run(params)
         A, B = be.factors()
         out[case] = (A.copy(), B.copy())
+        if case == "cg":    # rank the users right after the fit, each rank its share against its own replicas
+            out["topn"] = be.topN(10, output_score=True)
         del be
     q.put((rank, out))
     dist.barrier()
@@ -370,6 +372,13 @@ def test_two_gpu_sharded_matches_single_gpu(exchange):
         assert run_device(csr, csc, A, B, method, kw, flags=FLAG_NO_LOCKSTEP) == 0
         for r in (0, 1):
             assert np.array_equal(res[r][case][0], A) and np.array_equal(res[r][case][1], B), (case, r)
+        if case == "cg":
+            from poismf_b200 import c_funs
+            ids, sc = c_funs._topN_batch(A, B, top_n=10, output_score=True)
+            for r in (0, 1):
+                ids_r, sc_r = res[r]["topn"]
+                assert np.array_equal(sc_r, sc), r
+                assert all((sc[u] == sc[u][t]).sum() > 1 for u, t in zip(*np.nonzero(ids_r != ids)))
 
 
 def _two_gpu_topn_worker(rank, world, port, q):
@@ -675,6 +684,42 @@ def test_topn_fused_select_edge_cases(monkeypatch):
     ix3, sc3 = c_funs._topN_batch(A[:8], Bt, top_n=n_top, output_score=True)
     assert _lib.topn_stats(reset=True)[1] == 8
     assert all(len(set(r.tolist())) == n_top for r in ix3) and (sc3 == sc3[:, :1]).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_topn_against_resident_factors(dtype):
+    """pmf_b200_topN_fitted ranks against the factors held by a fit handle: same ids and scores as the
+    stateless batched entry on the same host arrays, same argument checks; after a sweep it ranks with the
+    UPDATED factors."""
+    from poismf_b200 import _lib, c_funs
+    from poismf_b200.device import DeviceFit
+    csr, csc, A0, B0, k = problem("pl2k", dtype)
+    rng = np.random.default_rng(3)
+    dimA, dimB = A0.shape[0], B0.shape[0]
+    users = rng.choice(dimA, 40, replace=False).astype(np.uint64)
+    lens = rng.integers(0, 5, users.shape[0])
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    eix = np.concatenate([rng.choice(dimB, int(m), replace=False) for m in lens] + [np.empty(0, np.int64)]).astype(np.uint64)
+    fit = DeviceFit(dimA, dimB, k, dtype)
+    fit.set_factors(A0, B0)
+    for kw in (dict(), dict(users=users, excl_ptr=ptr, excl_ix=eix)):
+        ix, sc = fit.topN(top_n=7, output_score=True, **kw)
+        ix2, sc2 = c_funs._topN_batch(A0, B0, top_n=7, output_score=True, **kw)
+        assert np.array_equal(sc, sc2)
+        assert all((sc[u] == sc[u][t]).sum() > 1 for u, t in zip(*np.nonzero(ix != ix2)))
+    with pytest.raises(ValueError):
+        fit.topN(users=np.array([dimA], np.uint64), top_n=3)
+    with pytest.raises(ValueError):
+        fit.topN(top_n=dimB + 1)
+    # after a fit the handle ranks with the fitted factors
+    fit.set_matrix(_lib.SIDE_CSR, *csr)
+    fit.set_matrix(_lib.SIDE_CSC, *csc)
+    fit.sweeps(_lib.make_params("cg", l2_reg=1e3, maxupd=5, numiter=2, limit_step=True))
+    A, B = fit.get_factors()
+    ix, sc = fit.topN(users=users, top_n=5, output_score=True)
+    ix2, sc2 = c_funs._topN_batch(A, B, users=users, top_n=5, output_score=True)
+    assert np.array_equal(sc, sc2) and not np.array_equal(A, A0)
+    assert all((sc[u] == sc[u][t]).sum() > 1 for u, t in zip(*np.nonzero(ix != ix2)))
 
 
 def test_topn_threshold_select_crowded_bin(monkeypatch):
