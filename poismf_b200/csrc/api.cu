@@ -1962,7 +1962,7 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                 CK(dmalloc(&tau, fchunk * sizeof(float))); take(tau);
                 CK(dmalloc(&cand_sc, fchunk * tc::CAND_CAP * sizeof(float))); take(cand_sc);
                 CK(dmalloc(&cand_id, fchunk * tc::CAND_CAP * sizeof(int))); take(cand_id);
-                CK(dmalloc(&cand_cnt, fchunk * sizeof(int))); take(cand_cnt);
+                CK(dmalloc(&cand_cnt, fchunk * 64 * sizeof(int))); take(cand_cnt);      // [user][region], regions <= 64
                 CK(dmalloc(&top_sc, fchunk * tc::CAND_TOP * sizeof(float))); take(top_sc);
                 CK(dmalloc(&top_id, fchunk * tc::CAND_TOP * sizeof(int))); take(top_id);
                 CK(dmalloc(&d_ovf, fchunk * sizeof(int))); take(d_ovf);
@@ -2003,6 +2003,7 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                     }
                     o.gmax = gmax; o.ngroups = ngroups; o.tau = tau;
                     o.cand_sc = cand_sc; o.cand_id = cand_id; o.cand_cnt = cand_cnt;
+                    o.cand_regions = 1; o.cand_cap = tc::CAND_CAP;
                     const dim3 tgrid((unsigned)ntiles, (unsigned)((m + tc::TM - 1) / tc::TM));
                     // pipelined scorer (persistent CTAs, TMA operands, two TMEM accumulators) unless disabled
                     CUtensorMap mapA, mapB;
@@ -2022,7 +2023,17 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                             if (eff > best + 0.02) { best = eff; chunks = c; }
                         }
                     }
-                    const int tiles_per_cta = (int)((ntiles + chunks - 1) / chunks);
+                    // The threshold pass visits every S-th item tile only: the M-th largest group maximum of a SAMPLE
+                    // of the items is a lower bound of the one over all items, so every wanted item still passes
+                    // tau; about S M items do (instead of M), which the candidate slots must hold (S M <= 1/4 of them)
+                    int S = 1;
+                    if (piped) {
+                        for (int c : {4, 2})
+                            if (ntiles >= (size_t)c * M_cand && (size_t)c * M_cand <= (size_t)tc::CAND_CAP / 4) { S = c; break; }
+                        if (const char* e = getenv("POISMF_B200_TOPN_SAMPLE")) S = std::max(1, std::min(atoi(e), 8));
+                        o.cand_regions = (int)chunks; o.cand_cap = tc::CAND_CAP / (int)chunks;
+                        o.ngroups = ((ntiles + S - 1) / S) * (tc::TN / tc::GROUP);
+                    }
                     const size_t pipe_smem = tc::pipe_smem_bytes(kpad);
                     const int pipe_stages = tc::pipe_stages(kpad);
                     if (piped) {
@@ -2031,22 +2042,23 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                         CK(cudaFuncSetAttribute(tc::score_pipe_tf32_kernel<tc::MODE_EMIT>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
                         tc::score_pipe_tf32_kernel<tc::MODE_GROUPMAX><<<dim3(chunks, ut), tc::PIPE_THREADS, pipe_smem>>>(
-                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, pipe_stages, o);
+                            mapA, mapB, (int)m, n, kpad, S, pipe_stages, o);
                     } else
                         tc::score_tiles_tf32_kernel<tc::MODE_GROUPMAX><<<tgrid, 128, (size_t)kpad * 1024>>>(
                             (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
                     LAUNCHED();
-                    tc::select_threshold_kernel<<<(unsigned)m, 256>>>(gmax, ngroups, M_cand, tau);
+                    tc::select_threshold_kernel<<<(unsigned)m, 256>>>(gmax, o.ngroups, M_cand, tau);
                     LAUNCHED();
-                    CK(cudaMemsetAsync(cand_cnt, 0, m * sizeof(int)));
+                    CK(cudaMemsetAsync(cand_cnt, 0, m * o.cand_regions * sizeof(int)));
                     if (piped)
                         tc::score_pipe_tf32_kernel<tc::MODE_EMIT><<<dim3(chunks, ut), tc::PIPE_THREADS, pipe_smem>>>(
-                            mapA, mapB, (int)m, n, kpad, tiles_per_cta, pipe_stages, o);
+                            mapA, mapB, (int)m, n, kpad, 1, pipe_stages, o);
                     else
                         tc::score_tiles_tf32_kernel<tc::MODE_EMIT><<<tgrid, 128, (size_t)kpad * 1024>>>(
                             (const float*)dAsel, (int)m, (const float*)dB, n, ldf, kpad, o);
                     LAUNCHED();
-                    tc::sort_candidates_kernel<<<(unsigned)m, 512>>>(cand_sc, cand_id, cand_cnt, top_sc, top_id, d_ovf);
+                    tc::sort_candidates_kernel<<<(unsigned)m, 512>>>(cand_sc, cand_id, cand_cnt, o.cand_regions, o.cand_cap,
+                                                                     top_sc, top_id, d_ovf);
                     LAUNCHED();
                     tc::rescore_select_kernel<<<(unsigned)m, 128>>>((const float*)dAsel, (const float*)dB, k, ldf, top_id,
                                                                     top_sc, (size_t)tc::CAND_TOP, M_cand, 0, (int)n_top,

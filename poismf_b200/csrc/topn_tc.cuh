@@ -136,6 +136,9 @@ struct TileOut {
     float* gmax; size_t ngroups;             // MODE_GROUPMAX: gmax[u, j / GROUP]
     const float* tau;                        // MODE_EMIT: per-user threshold ...
     float* cand_sc; int* cand_id; int* cand_cnt;   // ... and candidate lists (CAND_CAP slots per user)
+    // the pipelined scorer splits a user's slots into `cand_regions` regions of `cand_cap` slots, one per CTA
+    // along the items (each written by exactly one thread: no atomics); cand_cnt is [user][region]
+    int cand_regions, cand_cap;
 };
 
 // grid = (ceil(n/TN), ceil(U/TM)), 128 threads.
@@ -323,7 +326,7 @@ PMF_DEVINL uint64_t make_smem_desc_sw128(uint32_t saddr)
 template <int MODE>
 __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB, int U, size_t n,
-                                                              int kpad, int tiles_per_cta, int nstages, TileOut out)
+                                                              int kpad, int tile_stride, int nstages, TileOut out)
 {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the 128-byte swizzle works on 1024-byte atoms: align the operand area whatever the static variables take
@@ -337,9 +340,13 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
     unsigned char* sA = smem_raw;
     unsigned char* sB = smem_raw + (size_t)PIPE_UT * tile_bytes;
     const int u00 = blockIdx.y * (PIPE_UT * TM);
+    // the CTA's i-th item tile is tile (blockIdx.x + i gridDim.x) * tile_stride: the CTAs along x interleave over
+    // the items (popular items at low ids spread evenly over them), and with tile_stride > 1 only every
+    // tile_stride-th tile is visited (the threshold pass works on a sample of the items)
     const size_t ntiles = (n + TN - 1) / TN;
-    const size_t t0 = (size_t)blockIdx.x * tiles_per_cta;
-    const int nt = t0 < ntiles ? (int)((ntiles - t0) < (size_t)tiles_per_cta ? (ntiles - t0) : (size_t)tiles_per_cta) : 0;
+    const size_t nvisit = (ntiles + tile_stride - 1) / tile_stride;
+    const int nt = nvisit > blockIdx.x ? (int)((nvisit - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto visit = [&](int i) { return (size_t)blockIdx.x + (size_t)i * gridDim.x; };      // index among the visited tiles
 
     if (warp == 0) {   // two buffers of PIPE_UT accumulators of 128 columns: all 512 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
                 if (i >= nstages) pipe_wait(&stage_free[s], (uint32_t)((i / nstages - 1) & 1));
                 pipe_expect(&full[s], tile_bytes);
                 for (int bx = 0; bx < nbox; bx++)
-                    tma_box(sB + (size_t)s * tile_bytes + (size_t)bx * box_bytes, &mapB, bx * PIPE_BOXK, (int)((t0 + i) * TN), &full[s]);
+                    tma_box(sB + (size_t)s * tile_bytes + (size_t)bx * box_bytes, &mapB, bx * PIPE_BOXK, (int)(visit(i) * tile_stride * TN), &full[s]);
             }
         }
     } else if (warp == 8) {          // ---- MMA issuer ----
@@ -402,14 +409,17 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
     const float tau = (MODE == MODE_EMIT && u < U) ? out.tau[u] : 0.f;
     uint4 ex_next = make_uint4(0u, 0u, 0u, 0u);
     if (out.excl_bits && u < U && nt > 0)
-        ex_next = __ldg(reinterpret_cast<const uint4*>(out.excl_bits + (size_t)u * out.excl_words + ((t0 * TN) >> 5)));
+        ex_next = __ldg(reinterpret_cast<const uint4*>(out.excl_bits + (size_t)u * out.excl_words + ((visit(0) * tile_stride * TN) >> 5)));
+    int n_mine = 0;                                          // MODE_EMIT: candidates this thread has found
+    const size_t region = ((size_t)(u < U ? u : 0) * out.cand_regions + blockIdx.x) * out.cand_cap;
         for (int j = 0; j < nt; j++) {
             pipe_wait(&mma_done[j & 1], (uint32_t)((j >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const size_t j0 = (t0 + j) * TN;
+            const size_t j0 = visit(j) * tile_stride * TN;
             const uint4 ex = ex_next;                        // this user's exclusion bits of the tile's 128 items
             if (out.excl_bits && u < U && j + 1 < nt)        // (the next tile's are fetched a tile ahead)
-                ex_next = __ldg(reinterpret_cast<const uint4*>(out.excl_bits + (size_t)u * out.excl_words + ((j0 + TN) >> 5)));
+                ex_next = __ldg(reinterpret_cast<const uint4*>(out.excl_bits + (size_t)u * out.excl_words +
+                                                               ((visit(j + 1) * tile_stride * TN) >> 5)));
             float gm[8];                                     // MODE_GROUPMAX: the 8 group maxima of the 128 columns
             const uint32_t tcol = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((j & 1) * PIPE_UT + ut_mine) * TN);
             uint32_t ra[32], rb[32];
@@ -466,17 +476,17 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
 #pragma unroll
                             for (int e = 0; e < 2; e++) t[e] = (q & 8) ? t[2 * e + 1] : t[2 * e];
                             const uint32_t vb = (q & 16) ? t[1] : t[0];
-                            const int pos = atomicAdd(out.cand_cnt + u, 1);
-                            if (pos < CAND_CAP) {
-                                out.cand_sc[(size_t)u * CAND_CAP + pos] = __uint_as_float(vb);
-                                out.cand_id[(size_t)u * CAND_CAP + pos] = (int)(jc + q);
+                            if (n_mine < out.cand_cap) {       // this thread owns the region: plain stores
+                                out.cand_sc[region + n_mine] = __uint_as_float(vb);
+                                out.cand_id[region + n_mine] = (int)(jc + q);
                             }
+                            n_mine++;
                         }
                     }
                 }
             }
             if (MODE == MODE_GROUPMAX && u < U) {           // 8 consecutive group maxima: two 16-byte stores when they fit
-                const size_t gi = j0 / GROUP;
+                const size_t gi = visit(j) * (TN / GROUP);          // groups are numbered along the VISITED tiles
                 float* dst = out.gmax + (size_t)u * out.ngroups + gi;
                 if (gi + 8 <= out.ngroups && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                     reinterpret_cast<float4*>(dst)[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
@@ -485,6 +495,7 @@ __global__ void __launch_bounds__(PIPE_THREADS) score_pipe_tf32_kernel(const __g
                     for (int g = 0; g < 8; g++) if (gi + g < out.ngroups) dst[g] = gm[g];
             }
         }
+        if (MODE == MODE_EMIT && u < U) out.cand_cnt[(size_t)u * out.cand_regions + blockIdx.x] = n_mine;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -692,21 +703,35 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
 // overflow[u] = 1 when more than CAND_CAP items reached the threshold (ties at tau): redo exactly.
 __global__ void __launch_bounds__(512) sort_candidates_kernel(const float* __restrict__ cand_sc,
                                                               const int* __restrict__ cand_id,
-                                                              const int* __restrict__ cand_cnt,
+                                                              const int* __restrict__ cand_cnt, int regions, int cap,
                                                               float* __restrict__ top_sc, int* __restrict__ top_id,
                                                               int* __restrict__ overflow)
 {
     __shared__ float ss[CAND_CAP];
     __shared__ int si[CAND_CAP];
+    __shared__ int s_off[65];                        // where each region's candidates go (regions <= 64)
     const int u = blockIdx.x, tid = threadIdx.x;
-    const int cnt = cand_cnt[u];
     const float NEG = -RealTraits<float>::huge();
-    const int m = cnt < CAND_CAP ? cnt : CAND_CAP;
+    if (tid == 0) {
+        int off = 0, ovf = 0;
+        for (int r = 0; r < regions; r++) {
+            const int c = cand_cnt[(size_t)u * regions + r];
+            s_off[r] = off;
+            off += c < cap ? c : cap;
+            ovf |= c > cap;
+        }
+        s_off[regions] = off;
+        overflow[u] = ovf;
+    }
+    __syncthreads();
+    const int m = s_off[regions];                    // <= regions * cap <= CAND_CAP
     int len_pad = CAND_TOP;                          // sort only as much as is filled (power of two)
     while (len_pad < m) len_pad <<= 1;
-    for (int c = tid; c < len_pad; c += blockDim.x) {
-        ss[c] = c < m ? cand_sc[(size_t)u * CAND_CAP + c] : NEG;
-        si[c] = c < m ? cand_id[(size_t)u * CAND_CAP + c] : 0x7fffffff;
+    for (int c = m + tid; c < len_pad; c += blockDim.x) { ss[c] = NEG; si[c] = 0x7fffffff; }
+    for (int r = 0; r < regions; r++) {
+        const int o = s_off[r], c = s_off[r + 1] - o;
+        const size_t base = ((size_t)u * regions + r) * cap;
+        for (int t = tid; t < c; t += blockDim.x) { ss[o + t] = cand_sc[base + t]; si[o + t] = cand_id[base + t]; }
     }
     __syncthreads();
     for (int len = 2; len <= len_pad; len <<= 1)
@@ -725,7 +750,6 @@ __global__ void __launch_bounds__(512) sort_candidates_kernel(const float* __res
         top_sc[(size_t)u * CAND_TOP + c] = ss[c];
         top_id[(size_t)u * CAND_TOP + c] = si[c];
     }
-    if (tid == 0) overflow[u] = cnt > CAND_CAP ? 1 : 0;
 }
 
 __global__ void any_negative_kernel(const float* __restrict__ x, size_t n, int* __restrict__ flag)
