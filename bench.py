@@ -199,23 +199,38 @@ def bench_topn(args, rank, world, local_rank):
     lptr = (p64[lo:hi + 1] - p64[lo]).astype(np.uint64)
     leix = np.ascontiguousarray(eix[p64[lo]:p64[hi]])
 
+    # e2e: host buffers in and out.  N=1: the stateless batched entry (uploads A, B and the exclusion lists).
+    # N>1: the sharded public API on a persistent backend — every rank uploads 1/N of the factor rows (stored
+    # into all replicas over NVLink), ranks its share of the users against its replicas, reads its lists back
+    from poismf_b200.device import DeviceFit
+    be = None
+    if world > 1:
+        from poismf_b200.sharding import GpuBackend
+        be = GpuBackend(None, None, A, B, rank, world, local_rank)
+
     def one():
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
-        c_funs._topN_batch(A, B, users=users, excl_ptr=lptr, excl_ix=leix, top_n=t["top_n"], output_score=True)
+        if be is None:
+            c_funs._topN_batch(A, B, users=users, excl_ptr=lptr, excl_ix=leix, top_n=t["top_n"], output_score=True)
+        else:
+            be.reset(A, B)
+            be.topN(t["top_n"], excl_ptr=ptr, excl_ix=eix, output_score=True, gather=False)
         return time.perf_counter() - t0
     for _ in range(max(args.warmup, 1)):
         one()
     _lib.topn_stats(reset=True)
-    if dist is not None:
-        dist.barrier()
     ts = [one() for _ in range(args.steps)]
     n_tc, n_redo = _lib.topn_stats(reset=True)
-    ms = 1e3 * float(np.mean(ts))
-    # the same ranking against factors RESIDENT in a fit handle (pmf_b200_topN_fitted: what follows a fit on the
-    # device; every rank of a sharded fit holds full replicas): only ids and exclusion lists travel
-    from poismf_b200.device import DeviceFit
-    fit = DeviceFit(t["users"], t["items"], t["k"], np.float32, device=local_rank)
-    fit.set_factors(A, B)
+    ms_e2e = 1e3 * float(np.mean(ts))
+    # value: the same ranking against factors RESIDENT in a fit handle (pmf_b200_topN_fitted: what follows a fit
+    # on the device; every rank of a sharded fit holds full replicas): only ids and exclusion lists travel
+    if be is None:
+        fit = DeviceFit(t["users"], t["items"], t["k"], np.float32, device=local_rank)
+        fit.set_factors(A, B)
+    else:
+        fit = be.fit
 
     def one_resident():
         t0 = time.perf_counter()
@@ -225,11 +240,11 @@ def bench_topn(args, rank, world, local_rank):
         one_resident()
     if dist is not None:
         dist.barrier()
-    ms_res = 1e3 * float(np.mean([one_resident() for _ in range(args.steps)]))
+    ms = 1e3 * float(np.mean([one_resident() for _ in range(args.steps)]))
     if dist is not None:
-        tt = torch.tensor([ms, ms_res], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_res = float(tt[0].item()), float(tt[1].item())
+        ms, ms_e2e = float(tt[0].item()), float(tt[1].item())
     if rank == 0:
         peaks = {}
         try:
@@ -239,19 +254,27 @@ def bench_topn(args, rank, world, local_rank):
         # dense tf32 peak: half the measured bf16 cuBLAS figure (B200_PROFILING.md: 1.1 vs 2.25 PF nominal)
         peak = float(peaks.get("bf16_tflops", 1590.0)) / 2 * args.gpus          # all GPUs of the job
         flops = 2.0 * t["users"] * t["items"] * t["k"] * 2          # two scoring passes (threshold, candidates)
+        h2d = (A.nbytes + B.nbytes) // world + users.nbytes + lptr.nbytes + leix.nbytes if world > 1 else \
+            A.nbytes + B.nbytes + users.nbytes + lptr.nbytes + leix.nbytes
+        d2h = users.shape[0] * t["top_n"] * 12
         line = {"metric": "users ranked/sec (batched topN)", "value": t["users"] / (ms / 1e3), "unit": "users/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "tf32 candidates + f32 exact re-score", "data": "synthetic",
-                "config": {"workload": t["label"], "parallelism": f"users sharded x{args.gpus}, B replicated"},
+                "config": {"workload": t["label"], "parallelism": f"users sharded x{args.gpus}, B replicated",
+                           "value_call": "pmf_b200_topN_fitted: factors resident in a fit handle (HBM), ids + exclusion "
+                                         "lists up, rankings + scores down"},
                 "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                              "frac": flops / (ms / 1e3) / 1e12 / peak, "traffic": None,
-                             "note": "end-to-end call (upload of A, B and the exclusion lists, two TF32 scoring passes, exact "
-                                     "re-score, download) against half the measured bf16 cuBLAS peak of the job's GPUs"},
-                "resident": {"value": t["users"] / (ms_res / 1e3), "unit": "users/s", "ms_per_step": ms_res,
-                             "tensor_frac": flops / (ms_res / 1e3) / 1e12 / peak,
-                             "call": "pmf_b200_topN_fitted: factors resident in a fit handle, ids + exclusion lists up, "
-                                     "rankings + scores down"},
+                             "note": "whole resident call (threshold pass on 1/4 of the item tiles counted as a full "
+                                     "pass: 2 x 2 U n k flops) against half the measured bf16 cuBLAS peak of the job's GPUs"},
+                "e2e": {"value": t["users"] / (ms_e2e / 1e3), "unit": "users/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "call": ("pmf_b200_topN_batch: pageable host arrays A, B, exclusion lists in, rankings + scores out"
+                                 if world == 1 else
+                                 "GpuBackend.reset(A, B) + GpuBackend.topN(gather=False) on a persistent backend: every rank "
+                                 "uploads 1/N of the factor rows (stored into all replicas over NVLink), ranks its users, "
+                                 "reads its lists back (max over ranks; bytes are per rank)")},
                 "topn_users_on_tensor_cores": int(n_tc), "topn_users_redone_exactly": int(n_redo)}
         print(json.dumps(line))
     if dist is not None:

@@ -158,6 +158,11 @@ class GpuBackend:
         from . import _lib
         self.finish()
         world, rank = self.world, self.rank
+        if csr is None or csc is None:      # factors only (ranking with a model fitted elsewhere)
+            self.rangesA = self.rangesB = None
+            self.local_nnz = 0
+            self._set_factors(A0, B0)
+            return
         self.rangesA = self._ranges(csr[1])
         self.rangesB = self._ranges(csc[1])
         a0, a1 = self.rangesA[rank]
@@ -248,16 +253,17 @@ class GpuBackend:
         return self.fit.get_factors(*(out or (None, None)))
 
 
-    def topN(self, top_n, users=None, excl_ptr=None, excl_ix=None, output_score=False):
+    def topN(self, top_n, users=None, excl_ptr=None, excl_ix=None, output_score=False, gather=True):
         """Batched top-N after the fit, users split across the ranks: every rank ranks its share against ITS
         replicas of A and B (resident: pmf_b200_topN_fitted, no factor leaves or enters a GPU) and the per-user
-        lists are all-gathered.  Every rank returns the full (n_users x top_n) result."""
+        lists are all-gathered: every rank returns the full (n_users x top_n) result.  With gather=False a
+        rank returns the lists of its own share only (user_ranges(n_users, world)[rank])."""
         dimA, dimB, dt = self.fit.dimA, self.fit.dimB, self.fit.dtype
         scorer = lambda A_, B_, u_, p_, i_, n_, s_: self.fit.topN(users=u_, excl_ptr=p_, excl_ix=i_, top_n=n_,
                                                                   output_score=s_)
         return topn_sharded(np.empty((dimA, 0), dt), np.empty((dimB, 0), dt), top_n, users=users, excl_ptr=excl_ptr,
                             excl_ix=excl_ix, output_score=output_score, rank=self.rank, world=self.world,
-                            group=self.group, scorer=scorer)
+                            group=self.group, scorer=scorer, gather=gather)
 
 
 def user_ranges(n_users, nparts):
@@ -267,7 +273,7 @@ def user_ranges(n_users, nparts):
 
 
 def topn_sharded(A, B, top_n, users=None, excl_ptr=None, excl_ix=None, output_score=False, rank=0, world=1,
-                 group=None, scorer=None):
+                 group=None, scorer=None, gather=True):
     """Batched topN with the USERS split across ranks: B is replicated, every rank ranks
     its own contiguous range of users on its GPU, and the per-user lists are all-gathered — no exchange
     inside the scoring.  Every rank returns the full (n_users x top_n) result.
@@ -291,7 +297,7 @@ def topn_sharded(A, B, top_n, users=None, excl_ptr=None, excl_ix=None, output_sc
     else:
         ids = np.empty((0, top_n), np.uint64)
         sc = np.empty((0, top_n) if output_score else (0, 0), B.dtype)
-    if world == 1:
+    if world == 1 or not gather:
         return ids, sc
     import torch.distributed as dist
     parts = [None] * world
