@@ -4,15 +4,18 @@
 // (/root/reference/src/topN.c:215-224 does it as one GEMV per user).  Batched over users it is a
 // GEMM; here it runs on the 5th-generation tensor cores in TF32:
 //
-//   * one CTA per 128 users x 128 items tile; both operand tiles are staged K-major in shared
-//     memory in the canonical no-swizzle UMMA layout (8-row x 16-byte core matrices; for tile
-//     row r and 16-byte K-chunk c the chunk sits at (c * 128 + r) * 16 bytes, i.e. stride-byte-
-//     offset 128 B between 8-row groups, leading-byte-offset 2048 B between K-chunks),
-//   * one elected thread issues k/8 `tcgen05.mma.cta_group::1.kind::tf32` instructions
-//     (M = 128, N = 128, K = 8 each) accumulating into 128 TMEM columns, then
-//     `tcgen05.commit` onto an mbarrier,
-//   * the four warps read their 32 TMEM lanes back with `tcgen05.ld.32x32b.x32` and write the
-//     scores.
+// Two scorers share the epilogue logic:
+//   * `score_pipe_tf32_kernel` (the product path): warp-specialised persistent CTAs, operands by TMA
+//     (128-byte-swizzled 2-D boxes), a ring of shared-memory stages, accumulators double-buffered in TMEM,
+//     eight epilogue warps — described in front of the kernel;
+//   * `score_tiles_tf32_kernel` (r1; MODE_SCORES for the full-sort path and POISMF_B200_TOPN_NOPIPE): one CTA per
+//     128 users x 128 items tile; both operand tiles staged K-major in shared memory with generic loads in the
+//     canonical no-swizzle UMMA layout (8-row x 16-byte core matrices; for tile row r and 16-byte K-chunk c
+//     the chunk sits at (c * 128 + r) * 16 bytes, i.e. stride-byte-offset 128 B between 8-row groups,
+//     leading-byte-offset 2048 B between K-chunks); one elected thread issues k/8
+//     `tcgen05.mma.cta_group::1.kind::tf32` instructions (M = 128, N = 128, K = 8 each) accumulating into 128
+//     TMEM columns, then `tcgen05.commit` onto an mbarrier; the four warps read their 32 TMEM lanes back with
+//     `tcgen05.ld.32x32b.x32`.
 //
 // TF32 scores are only used to pick CANDIDATES: the caller keeps the best 2N+ per user, re-scores
 // them exactly in FP32 (same left-to-right sums as the reference) and proves from the TF32 error
@@ -21,10 +24,11 @@
 //
 // The select is fused into the scorer's epilogue so that the U x n score matrix never exists
 // (SURVEY.md 8d).  Two passes over the tiles, the GEMM being far cheaper than any sort of n scores:
-//   pass 1 (MODE_GROUPMAX)  per user, the maximum of every group of 16 consecutive items
-//           -> tau[u] = the M-th largest group maximum (radix select over n/16 values): at least M
-//              items score >= tau[u], and at most 16 M of them unless scores tie at tau[u];
-//   pass 2 (MODE_EMIT)      items with score >= tau[u] are appended to the user's candidate list,
+//   pass 1 (MODE_GROUPMAX)  per user, the maximum of every group of 16 consecutive items — of every S-th item
+//           tile only (pipelined scorer; S = 4, 2 or 1)
+//           -> tau[u] = the M-th largest of these group maxima: a lower bound of the M-th largest over all
+//              items, so at least M items score >= tau[u], and about S M of them do;
+//   pass 2 (MODE_EMIT)      all tiles; items with score >= tau[u] are appended to the user's candidate list,
 // then the (<= 4096) candidates are ordered by (score desc, id asc) and the best M go to the exact
 // re-scoring as before.  Excluded items are masked in the epilogue from a per-user bitmap.
 #pragma once
