@@ -265,7 +265,13 @@ def _gloo_topn_worker(rank, world, port, q):
     ids, sc = topn_sharded(A, B, n_top, users=users, excl_ptr=ptr, excl_ix=eix, output_score=True, rank=rank,
                            world=world, scorer=cpu_scorer)
     ids1, sc1 = topn_sharded(A, B, n_top, users=users, excl_ptr=ptr, excl_ix=eix, output_score=True, scorer=cpu_scorer)
-    q.put((rank, bool(np.array_equal(ids, ids1) and np.array_equal(sc, sc1) and ids.shape == (30, n_top))))
+    # gather=False: a rank keeps the lists of its own share of the users
+    from poismf_b200.sharding import user_ranges
+    ids_l, sc_l = topn_sharded(A, B, n_top, users=users, excl_ptr=ptr, excl_ix=eix, output_score=True, rank=rank,
+                               world=world, scorer=cpu_scorer, gather=False)
+    lo, hi = user_ranges(users.shape[0], world)[rank]
+    local_ok = np.array_equal(ids_l, ids1[lo:hi]) and np.array_equal(sc_l, sc1[lo:hi])
+    q.put((rank, bool(np.array_equal(ids, ids1) and np.array_equal(sc, sc1) and ids.shape == (30, n_top) and local_ok)))
     dist.destroy_process_group()
 
 
