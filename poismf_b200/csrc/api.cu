@@ -1942,7 +1942,7 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             // ---- fused select (topn_tc.cuh): no score matrix; two passes over the tensor-core tiles ----
             const size_t words = ntiles * 4;     // exclusion bitmap: 128 bits per tile and user
             const bool have_excl = excl_ptr && excl_ix;
-            const size_t per_user = ngroups * 4 + (have_excl ? words * 4 : 0) + (size_t)tc::CAND_CAP * 8 +
+            const size_t per_user = ngroups * 4 + (have_excl ? words * 4 : 0) + (size_t)tc::CAND_SLACK * tc::CAND_CAP * 8 +
                                     (size_t)tc::CAND_TOP * 8 + pitch + n_top * 12 + 64;
             // users per batch: a quarter of the free device memory, at most 32 GB, for the per-user work arrays
             size_t mem_free = 0, mem_total = 0;
@@ -1960,8 +1960,8 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                 CK(dmalloc(&dusers, fchunk * sizeof(long long)));
                 CK(dmalloc(&gmax, fchunk * ngroups * sizeof(float))); take(gmax);
                 CK(dmalloc(&tau, fchunk * sizeof(float))); take(tau);
-                CK(dmalloc(&cand_sc, fchunk * tc::CAND_CAP * sizeof(float))); take(cand_sc);
-                CK(dmalloc(&cand_id, fchunk * tc::CAND_CAP * sizeof(int))); take(cand_id);
+                CK(dmalloc(&cand_sc, fchunk * tc::CAND_SLACK * tc::CAND_CAP * sizeof(float))); take(cand_sc);
+                CK(dmalloc(&cand_id, fchunk * tc::CAND_SLACK * tc::CAND_CAP * sizeof(int))); take(cand_id);
                 CK(dmalloc(&cand_cnt, fchunk * 64 * sizeof(int))); take(cand_cnt);      // [user][region], regions <= 64
                 CK(dmalloc(&top_sc, fchunk * tc::CAND_TOP * sizeof(float))); take(top_sc);
                 CK(dmalloc(&top_id, fchunk * tc::CAND_TOP * sizeof(int))); take(top_id);
@@ -2031,7 +2031,9 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
                         for (int c : {4, 2})
                             if (ntiles >= (size_t)c * M_cand && (size_t)c * M_cand <= (size_t)tc::CAND_CAP / 4) { S = c; break; }
                         if (const char* e = getenv("POISMF_B200_TOPN_SAMPLE")) S = std::max(1, std::min(atoi(e), 8));
-                        o.cand_regions = (int)chunks; o.cand_cap = tc::CAND_CAP / (int)chunks;
+                        o.cand_regions = (int)chunks;
+                        // (4x the even share: a user's candidates may cluster in a few tiles)
+                        o.cand_cap = std::min(tc::CAND_CAP, tc::CAND_SLACK * tc::CAND_CAP / (int)chunks);
                         o.ngroups = ((ntiles + S - 1) / S) * (tc::TN / tc::GROUP);
                     }
                     const size_t pipe_smem = tc::pipe_smem_bytes(kpad);

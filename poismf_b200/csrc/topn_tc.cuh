@@ -41,7 +41,8 @@ namespace tc {
 constexpr int TM = 128;   // users per tile  (UMMA M)
 constexpr int TN = 128;   // items per tile  (UMMA N)
 constexpr int GROUP = 16;        // items per group maximum
-constexpr int CAND_CAP = 4096;   // candidate slots per user (>= GROUP * 256)
+constexpr int CAND_CAP = 4096;   // candidates per user that are ordered (>= GROUP * 256)
+constexpr int CAND_SLACK = 4;    // the per-CTA regions of a user hold CAND_SLACK x CAND_CAP slots together
 constexpr int CAND_TOP = 256;    // candidates handed to the exact re-scoring (>= M)
 enum { MODE_SCORES = 0, MODE_GROUPMAX = 1, MODE_EMIT = 2 };
 
@@ -723,12 +724,13 @@ __global__ void __launch_bounds__(512) sort_candidates_kernel(const float* __res
             s_off[r] = off;
             off += c < cap ? c : cap;
             ovf |= c > cap;
+            if (off > CAND_CAP) { off = CAND_CAP; ovf = 1; }      // more than can be ordered here: exact fallback
         }
         s_off[regions] = off;
         overflow[u] = ovf;
     }
     __syncthreads();
-    const int m = s_off[regions];                    // <= regions * cap <= CAND_CAP
+    const int m = s_off[regions];                    // <= CAND_CAP
     int len_pad = CAND_TOP;                          // sort only as much as is filled (power of two)
     while (len_pad < m) len_pad <<= 1;
     for (int c = m + tid; c < len_pad; c += blockDim.x) { ss[c] = NEG; si[c] = 0x7fffffff; }

@@ -722,6 +722,29 @@ def test_topn_against_resident_factors(dtype):
     assert all((sc[u] == sc[u][t]).sum() > 1 for u, t in zip(*np.nonzero(ix != ix2)))
 
 
+def test_topn_candidates_clustered_in_few_tiles():
+    """Every user's best items are the same 800 consecutive ids (6 item tiles): the sampled threshold pass sees
+    only two of those tiles, so all 800 become candidates and they land in a handful of the per-CTA candidate
+    regions — the regions' slack must hold them (no exact fallback), rankings equal the oracle's."""
+    from poismf_b200 import _lib, c_funs
+    rng = np.random.default_rng(8)
+    k, n_items, n_users, n_top = 24, 30_000, 200, 10
+    A = np.ascontiguousarray(rng.gamma(2.0, 0.5, size=(n_users, k)).astype(np.float32))
+    B = rng.gamma(2.0, 0.05, size=(n_items, k))
+    B[:800] *= 40.0
+    B = np.ascontiguousarray(B.astype(np.float32))
+    _lib.topn_stats(reset=True)
+    ix, sc = c_funs._topN_batch(A, B, top_n=n_top, output_score=True)
+    n_tc, n_redo = _lib.topn_stats(reset=True)
+    assert n_tc == n_users and n_redo == 0, (n_tc, n_redo)
+    assert (ix < 800).all()
+    orc = Restatement(np.float32)
+    for u in range(0, n_users, 17):
+        rc, ix_r, sc_r = orc.topN(np.ascontiguousarray(A[u]), B, n_top)
+        assert rc == 0 and np.array_equal(sc[u], sc_r)
+        assert all((sc_r == sc_r[t]).sum() > 1 for t in np.nonzero(ix[u] != ix_r)[0])
+
+
 def test_topn_threshold_select_crowded_bin(monkeypatch):
     """More group maxima in the threshold's histogram bin than the select's shared-memory list holds (70k items
     whose scores lie within 0.1 % of each other): the threshold falls back to the bin's lower edge, every item
