@@ -459,6 +459,15 @@ def main():
             roof["tile_passes_per_row_max"] = passes
             roof["onchip_tile_GBps_upper"] = 2 * nnz * k * s * passes / (ms_step / 1e3) / 1e9
 
+    # every rank's own work per sweep (its bins' device times of the per-launch pass, by side): the shards' balance
+    shard_work = None
+    if world > 1 and prof:
+        mine = torch.tensor([sum(p["ms"] for p in prof if p["side"] == sd) / args.steps for sd in (0, 1)],
+                            device="cuda", dtype=torch.float64)
+        allw = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allw, mine)
+        shard_work = [[round(float(w[0]), 4), round(float(w[1]), 4)] for w in allw]
+
     # ---- N > 1: every rank hashes its replicas; rank 0 repeats the sweeps on one GPU
     parity = None
     if world > 1 and not args.no_parity:
@@ -605,6 +614,9 @@ def main():
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
         if e2e_pageable is not None:
             line["e2e_pageable"] = e2e_pageable
+        if shard_work is not None:
+            line["shard_work_ms"] = {"per_rank_A_B": shard_work,
+                                     "note": "sum of a rank's own launches per sweep, serialised (per-launch pass)"}
         if parity is not None:
             line["parity"] = parity
         print(json.dumps(line))

@@ -18,6 +18,8 @@ the CPU tests, where the row solver is stood in by a caller-supplied function).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -26,6 +28,15 @@ def row_cost(nnz_per_row):
     ~10 non-zero-equivalents of fixed work per row, and non-zeros of long rows cost more — rows beyond
     one CTA's shared memory pay cluster barriers (x2), rows streamed from L2 more again (x3)."""
     n = np.asarray(nnz_per_row).astype(np.float64)
+    spec = os.environ.get("POISMF_B200_ROW_COST")      # tuning: "fixed,b1:f1,b2:f2,..." = fixed + n * f_i for n > b_i
+    if spec:
+        parts = spec.split(",")
+        c = n + float(parts[0])
+        for item in parts[1:]:
+            b, f = item.split(":")
+            c += n * ((n > float(b)) * float(f))       # f = the factor ADDED above the break
+        c[n <= 0] = 0.0
+        return c
     c = n + 10.0                        # (in-place arithmetic: this runs inside every sharded load)
     c += n * (n > 1000)
     c += n * (n > 16000)
