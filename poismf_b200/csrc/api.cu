@@ -1942,7 +1942,10 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             // ---- fused select (topn_tc.cuh): no score matrix; two passes over the tensor-core tiles ----
             const size_t words = ntiles * 4;     // exclusion bitmap: 128 bits per tile and user
             const bool have_excl = excl_ptr && excl_ix;
-            const size_t per_user = ngroups * 4 + (have_excl ? words * 4 : 0) + (size_t)tc::CAND_SLACK * tc::CAND_CAP * 8 +
+            // group maxima per user: whole tiles (the pipelined scorer numbers 8 groups per visited tile, the last
+            // tile's groups beyond n included)
+            const size_t ngroups_alloc = ntiles * (tc::TN / tc::GROUP);
+            const size_t per_user = ngroups_alloc * 4 + (have_excl ? words * 4 : 0) + (size_t)tc::CAND_SLACK * tc::CAND_CAP * 8 +
                                     (size_t)tc::CAND_TOP * 8 + pitch + n_top * 12 + 64;
             // users per batch: a quarter of the free device memory, at most 32 GB, for the per-user work arrays
             size_t mem_free = 0, mem_total = 0;
@@ -1958,7 +1961,7 @@ static int topn_batch_impl(const real* A, const real* B, int k, const IX* user_i
             auto fused = [&]() -> int {
                 CK(dmalloc(&dAsel, fchunk * pitch));
                 CK(dmalloc(&dusers, fchunk * sizeof(long long)));
-                CK(dmalloc(&gmax, fchunk * ngroups * sizeof(float))); take(gmax);
+                CK(dmalloc(&gmax, fchunk * ngroups_alloc * sizeof(float))); take(gmax);
                 CK(dmalloc(&tau, fchunk * sizeof(float))); take(tau);
                 CK(dmalloc(&cand_sc, fchunk * tc::CAND_SLACK * tc::CAND_CAP * sizeof(float))); take(cand_sc);
                 CK(dmalloc(&cand_id, fchunk * tc::CAND_SLACK * tc::CAND_CAP * sizeof(int))); take(cand_id);
