@@ -289,3 +289,28 @@ def test_topn_user_sharding_gloo_world2():
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
 
+
+
+def test_shard_ranges_are_remembered_per_offsets_array():
+    """GpuBackend.load computes the cost-balanced shard boundaries once per offsets array (address, length, sampled
+    content); another array, or the same buffer with other content, gets its own."""
+    from poismf_b200.sharding import GpuBackend, nnz_balanced_ranges, row_cost
+    be = GpuBackend.__new__(GpuBackend)          # host logic only: no device
+    be.world = 3
+    rng = np.random.default_rng(0)
+    ptr = np.concatenate([[0], np.cumsum(rng.integers(0, 50, 5000))]).astype(np.uint64)
+    r1 = be._ranges(ptr)
+    assert r1 == nnz_balanced_ranges(ptr, 3) and be._ranges(ptr) is r1
+    ptr2 = ptr.copy()
+    assert be._ranges(ptr2) == r1 and be._ranges(ptr2) is not r1
+    ptr[1:] += np.arange(1, ptr.shape[0], dtype=np.uint64) * 40          # same buffer, other content
+    r3 = be._ranges(ptr)
+    assert r3 == nnz_balanced_ranges(ptr, 3) and r3 != r1
+    # the tunable cost model reproduces the default one
+    n = np.array([0, 5, 600, 2000, 20000])
+    base = row_cost(n)
+    os.environ["POISMF_B200_ROW_COST"] = "10,1000:1,16000:1"
+    try:
+        assert np.array_equal(row_cost(n), base)
+    finally:
+        del os.environ["POISMF_B200_ROW_COST"]
